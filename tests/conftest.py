@@ -1,0 +1,63 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+@pytest.fixture(scope="session")
+def restatement():
+    import oracle
+    return oracle.restatement()
+
+
+@pytest.fixture(scope="session")
+def ref_camera():
+    import oracle
+    r = oracle.ref_camera()
+    if r is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference): golden fixtures cover this")
+    return r
+
+
+@pytest.fixture(scope="session")
+def ref_client():
+    import oracle
+    r = oracle.ref_client()
+    if r is None:
+        pytest.skip("oracle/_ref not built")
+    return r
+
+
+@pytest.fixture(scope="session")
+def ref_optimized():
+    import oracle
+    r = oracle.ref_optimized()
+    if r is None:
+        pytest.skip("oracle/_ref not built")
+    return r
+
+
+def roundtrip_inputs():
+    """The inputs of tests/golden/roundtrip_all_int16.npz (make_golden.py)."""
+    allv = np.zeros((65536, 5), np.int16)
+    allv[:, 0] = np.arange(-32768, 32768)
+    allv[:, 1] = allv[::-1, 0]
+    allv[:, 2] = np.roll(allv[:, 0], 12345)
+    allv[:, 3] = np.arange(65536).astype(np.uint16).view(np.int16)
+    allv[:, 4] = (np.arange(65536) % 251).astype(np.int16)
+    return allv
