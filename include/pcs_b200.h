@@ -1,0 +1,205 @@
+/* pcs_b200.h -- C ABI of the B200-native point-cloud stitching hot path.
+ *
+ * Drop-in boundary for conix-center/pointcloud_stitching.  The reference has no
+ * plugin/FFI layer: its seam is a handful of free functions called from main()
+ * (SURVEY.md s8b).  Each entry point below names the reference function it
+ * replaces (file:line relative to the reference checkout) and keeps that
+ * function's buffer layout byte for byte:
+ *
+ *   wire record   10 bytes  [x_mm:i16][y_mm:i16][z_mm:i16][R:u8][G:u8][B:u8][0:u8]
+ *                           (src/pcs-camera-optimized.cpp:581-585)
+ *   camera buffer [int32 payload_bytes][records...]   payload at byte offset 4
+ *                           (src/pcs-camera-optimized.cpp:690,715-719)
+ *   stitched buf  [int32 payload_bytes][cam0 records][cam1 records]...
+ *                           (src/pcs-multicamera-client.cpp:378,385-395)
+ *
+ * Plain C types only; no torch / CUDA types in any signature (CUDA streams are
+ * passed as void*).  Every function returns >= 0 on success (a count or a byte
+ * size, as the reference function does) and a negative pcs_status on failure;
+ * nothing here ever calls exit().  There is NO CPU fallback: without a CUDA
+ * device pcs_b200_create() fails with PCS_ERR_CUDA.
+ *
+ * Pointer conventions: `*_host` arguments are ordinary host memory (pinned or
+ * pageable); `*_dev` arguments are device memory on the context's GPU.  Device
+ * frame / payload pointers must be 16-byte aligned (cudaMalloc and torch
+ * allocations are).  To get a 16-byte aligned payload inside a
+ * [int32][records] buffer, place the buffer at (aligned allocation + 12).
+ */
+#ifndef PCS_B200_H
+#define PCS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PCS_API __attribute__((visibility("default")))
+#else
+#define PCS_API
+#endif
+
+#define PCS_B200_ABI_VERSION 1
+#define PCS_B200_RECORD_BYTES 10
+#define PCS_B200_HEADER_BYTES 4
+/* src/pcs-camera-optimized.cpp:27,157,673: short[BUF_SIZE] buffer, memset(BUF_SIZE bytes) */
+#define PCS_B200_CAMERA_BUF_SHORTS 5000000
+
+typedef struct pcs_ctx pcs_ctx;
+typedef struct pcs_batch pcs_batch;
+
+typedef enum pcs_status {
+    PCS_OK = 0,
+    PCS_ERR_INVALID = -1,     /* bad argument (null, misaligned, n % 4 != 0, unknown stream ...) */
+    PCS_ERR_CUDA = -2,        /* CUDA runtime / driver error, or no device; see pcs_b200_last_error */
+    PCS_ERR_NOMEM = -3,
+    PCS_ERR_UNSUPPORTED = -4,
+    PCS_ERR_CAPACITY = -5     /* output does not fit the buffer given */
+} pcs_status;
+
+/* rs2_intrinsics without the distortion model (D400: all coefficients zero). */
+typedef struct pcs_intrinsics {
+    int32_t width, height;
+    float ppx, ppy, fx, fy;
+} pcs_intrinsics;
+
+/* Everything the reference keeps in compile-time constants and globals
+ * (tf_mat src/pcs-camera-optimized.cpp:64-67; cutoff bounds :398-401; cached
+ * geometry :369-377) plus what librealsense holds for rs2::pointcloud. */
+typedef struct pcs_stream_desc {
+    pcs_intrinsics depth;      /* z16 frame geometry; width % 8 == 0 */
+    pcs_intrinsics color;      /* colour frame geometry */
+    float d2c_rotation[9];     /* depth -> colour extrinsics, column-major (rs2_extrinsics) */
+    float d2c_translation[3];  /* metres */
+    float depth_scale;         /* metres per z16 unit (0.001 on D400) */
+    int32_t color_bpp;         /* bytes per colour pixel, >= 3; R,G,B are bytes 0,1,2 */
+    int32_t color_stride;      /* bytes per colour row */
+    float tf[16];              /* camera -> world, row-major 4x4, row 3 ignored */
+    int32_t cutoff;            /* -c: keep only z in (z_lo, z_hi], x in (x_lo, x_hi] (pre-transform) */
+    float z_lo, z_hi, x_lo, x_hi; /* reference: 0, 1.5, -2, 2 */
+    int32_t cutoff_lane_reversed; /* 1 = reproduce the reference's reversed mask lanes */
+} pcs_stream_desc;
+
+typedef struct pcs_config {
+    int32_t device;            /* CUDA device ordinal */
+    int32_t max_streams;       /* camera streams this context serves (>= 1) */
+    int32_t kernel_variant;    /* 0 = auto, 1 = direct (LDG/STG), 2 = bulk-async pipelined (TMA) */
+    int32_t reserved;
+} pcs_config;
+
+/* One frame of work for the batched device-resident path. */
+typedef struct pcs_frame_job {
+    int32_t stream;            /* index given to pcs_b200_set_stream */
+    int32_t reserved;
+    const uint16_t *z16_dev;   /* depth.height * depth.width */
+    const uint8_t *color_dev;  /* color.height * color_stride bytes */
+    int16_t *payload_dev;      /* depth.width*depth.height records (10 B each) */
+    float *xyzrgb_dev;         /* optional: N x {x,y,z metres (transformed), b,g,r,255} 16 B/pt; or NULL */
+    int32_t *count_dev;        /* optional: receives the record count (needed with cutoff); or NULL */
+} pcs_frame_job;
+
+PCS_API int pcs_b200_abi_version(void);
+PCS_API const char *pcs_b200_status_string(int status);
+
+/* Lifetime.  Replaces the process-lifetime malloc/free of the reference mains
+ * (src/pcs-camera-optimized.cpp:157,345; src/pcs-multicamera-client.cpp:499,554). */
+PCS_API int pcs_b200_create(const pcs_config *cfg, pcs_ctx **out);
+PCS_API void pcs_b200_destroy(pcs_ctx *ctx);
+/* Message of the last failure on this context (thread-local when ctx is NULL). */
+PCS_API const char *pcs_b200_last_error(const pcs_ctx *ctx);
+
+/* Replaces the globals behind `initialized` (src/pcs-camera-optimized.cpp:349-409)
+ * and the hard-coded transform (:64-72).  May be called again at any time. */
+PCS_API int pcs_b200_set_stream(pcs_ctx *ctx, int stream, const pcs_stream_desc *desc);
+
+/* ---- camera side, host buffers (what the reference's main() calls) ---------- */
+
+/* Replaces rs2::pointcloud::calculate + sendXYZRGBPointcloud
+ * (src/pcs-camera-optimized.cpp:288-292,669-723): depth + colour frame in,
+ * the reference's camera buffer image out.  buffer_host is short[5 000 000]:
+ * bytes [0,5 000 000) are zeroed, records start at byte 4, and with
+ * write_header != 0 (-s) the int32 payload size is stored at byte 0.
+ * Returns the payload size in bytes (:697,722). */
+PCS_API int pcs_b200_send_xyzrgb(pcs_ctx *ctx, int stream, const uint16_t *z16_host,
+                         const uint8_t *color_host, int16_t *buffer_host, int write_header);
+
+/* The same call split in two so one host thread can keep several camera streams in
+ * flight: begin() enqueues H2D + kernel + D2H on the stream's own CUDA stream and
+ * returns; end() waits and finishes the buffer image.  The copies only overlap when
+ * the host buffers are pinned (pcs_b200_host_alloc).  Calls on distinct `stream`
+ * ids are thread-safe; one begin/end pair may be outstanding per stream. */
+PCS_API int pcs_b200_send_xyzrgb_begin(pcs_ctx *ctx, int stream, const uint16_t *z16_host,
+                               const uint8_t *color_host, int16_t *buffer_host, int write_header);
+PCS_API int pcs_b200_send_xyzrgb_end(pcs_ctx *ctx, int stream);
+
+/* Page-locked host memory for the calls above (cudaHostAlloc / cudaFreeHost). */
+PCS_API void *pcs_b200_host_alloc(pcs_ctx *ctx, size_t bytes);
+PCS_API void pcs_b200_host_free(pcs_ctx *ctx, void *p);
+
+/* Replaces copyPointCloudXYZRGBToBufferSIMD (src/pcs-camera-optimized.cpp:363-616):
+ * same inputs as the reference function (rs2::vertex[n], rs2::texture_coordinate[n],
+ * colour frame), records out.  n % 4 == 0.  Returns the record count (:612-615). */
+PCS_API int pcs_b200_pack_from_vertices(pcs_ctx *ctx, int stream, const float *xyz_host,
+                                const float *uv_host, int n, const uint8_t *color_host,
+                                int16_t *payload_host);
+
+/* ---- camera side, device-resident and batched ------------------------------- */
+
+/* Same work as pcs_b200_send_xyzrgb's kernel for many frames in one launch.
+ * The job table is captured once; run() only launches.  cuda_stream is a
+ * cudaStream_t (NULL = default stream). */
+PCS_API int pcs_b200_batch_create(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs, pcs_batch **out);
+PCS_API int pcs_b200_batch_run(pcs_ctx *ctx, pcs_batch *batch, void *cuda_stream);
+PCS_API void pcs_b200_batch_destroy(pcs_ctx *ctx, pcs_batch *batch);
+/* Number of kernel launches one batch_run issues (for launch accounting). */
+PCS_API int pcs_b200_batch_launches(const pcs_batch *batch);
+
+/* Device-pointer form of pcs_b200_pack_from_vertices. */
+PCS_API int pcs_b200_pack_from_vertices_dev(pcs_ctx *ctx, int stream, const float *xyz_dev,
+                                    const float *uv_dev, int n, const uint8_t *color_dev,
+                                    int16_t *payload_dev, int32_t *count_dev, void *cuda_stream);
+
+/* ---- stitch side ------------------------------------------------------------- */
+
+/* Replaces the concat loop of sendStitchToUnity (src/pcs-multicamera-client.cpp:385-395):
+ * for each camera in order, every `downsample`-th record is appended at
+ * stitched + 4; the int32 total is stored at stitched + 0.  n_shorts[i] is the
+ * camera's payload length in shorts (as readCloud leaves it, :368).
+ * Returns the stitched payload bytes. */
+PCS_API int pcs_b200_stitch_raw_dev(pcs_ctx *ctx, const int16_t *const *payload_dev, const int32_t *n_shorts,
+                            int n_cams, int downsample, uint8_t *stitched_dev, size_t stitched_cap,
+                            void *cuda_stream);
+PCS_API int pcs_b200_stitch_raw(pcs_ctx *ctx, const int16_t *const *payload_host, const int32_t *n_shorts,
+                        int n_cams, int downsample, uint8_t *stitched_host, size_t stitched_cap);
+
+/* Replaces updateCloudXYZRGB -> `+=` -> convertPointCloudXYZRGBToBuffer
+ * (src/pcs-multicamera-optimized.cpp:226-265,288-289,364-367,308-310): per camera
+ * unpack (int16 / 1000.0f), decimate, 4x4 transform, ordered append, repack
+ * (truncate(x * 1000.0f)).  transforms = n_cams x 16 floats row-major (host).
+ * cloud32_dev, when not NULL, also receives the stitched cloud as 32-byte
+ * pcl::PointXYZRGB records.  Returns the stitched payload bytes. */
+PCS_API int pcs_b200_stitch_pcl_dev(pcs_ctx *ctx, const int16_t *const *payload_dev, const int32_t *n_shorts,
+                            int n_cams, int downsample, const float *transforms,
+                            uint8_t *stitched_dev, size_t stitched_cap, void *cloud32_dev,
+                            void *cuda_stream);
+PCS_API int pcs_b200_stitch_pcl(pcs_ctx *ctx, const int16_t *const *payload_host, const int32_t *n_shorts,
+                        int n_cams, int downsample, const float *transforms,
+                        uint8_t *stitched_host, size_t stitched_cap);
+
+/* Voxel-grid merge of n records (own integer specification, oracle/SPEC.md s3; the
+ * reference includes pcl/filters/voxel_grid.h but never calls it).  Returns the
+ * number of voxels written to out_dev (capacity n records). */
+PCS_API int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
+                             int16_t *out_dev, void *cuda_stream);
+PCS_API int pcs_b200_voxel_merge(pcs_ctx *ctx, const int16_t *records_host, int n, int leaf_mm,
+                         int16_t *out_host);
+
+/* Blocks until everything issued on cuda_stream by this context has finished. */
+PCS_API int pcs_b200_synchronize(pcs_ctx *ctx, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCS_B200_H */

@@ -1,0 +1,807 @@
+// C ABI (include/pcs_b200.h) over the sm_100a kernels.  Host side in C++ like the
+// reference; no CPU compute path: every entry point either launches a kernel or
+// fails with a negative status.
+#include "../../include/pcs_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pcs_kernels.cuh"
+#include "pcs_k1_pipe.cuh"
+#include "pcs_voxel.cuh"
+
+using namespace pcs;
+
+// ---------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_tls_error;
+
+struct StreamState {
+    bool configured = false;
+    pcs_stream_desc desc{};
+    StreamParams params{};
+    cudaStream_t cs = nullptr;
+    std::mutex mu;
+    // ctx-owned device buffers for the host-pointer entry points
+    uint16_t *d_z16 = nullptr;
+    uint8_t *d_color = nullptr;
+    int16_t *d_payload = nullptr;   // N records (compacted when cutoff)
+    int16_t *d_dense = nullptr;     // cutoff scratch
+    uint8_t *d_keep = nullptr;
+    int32_t *d_tiles = nullptr;
+    int32_t *d_count = nullptr;
+    int32_t *h_count = nullptr;     // pinned
+    DevJob *d_job = nullptr;
+    size_t cap_pts = 0, cap_color = 0;
+    // vertices path
+    float *d_xyz = nullptr, *d_uv = nullptr;
+    int16_t *d_vpayload = nullptr;
+    size_t cap_vtx = 0;
+    // -c scratch of the vertices path
+    int16_t *d_cdense = nullptr;
+    uint8_t *d_ckeep = nullptr;
+    int32_t *d_ctiles = nullptr;
+    size_t cap_cut = 0;
+    // outstanding begin()
+    bool pending = false;
+    int16_t *pending_buffer = nullptr;
+    int pending_header = 0;
+};
+
+}  // namespace
+
+struct pcs_ctx {
+    int device = 0;
+    int max_streams = 0;
+    int kernel_variant = 0;
+    int sm_count = 0;
+    StreamState *streams = nullptr;
+    StreamParams *d_params = nullptr;
+    std::mutex mu;          // guards `error`
+    std::mutex scratch_mu;  // guards the stitch / voxel scratch below
+    std::string error;
+    // stitch-side scratch for the host-pointer entry points
+    uint8_t *d_stitch_in = nullptr, *d_stitch_out = nullptr;
+    size_t cap_stitch_in = 0, cap_stitch_out = 0;
+    VoxelScratch voxel;
+};
+
+struct pcs_batch {
+    std::vector<DevJob> jobs;          // host mirror
+    DevJob *d_jobs = nullptr;
+    struct Group {                      // one launch per kernel variant present
+        int tex_mode, cutoff, floatout;
+        int first, count;               // range in the (sorted) job table
+        int max_tiles;
+        int max_octets;
+    };
+    std::vector<Group> groups;
+    struct CutJob { int job, n, lane_rev, n_tiles; int32_t *d_tiles; };
+    std::vector<CutJob> cuts;
+    std::vector<void *> owned;          // scratch to free
+    int launches = 0;
+    PipeBatch pipe;                     // pipelined-kernel work list (variant 2)
+    bool use_pipe = false;
+};
+
+namespace {
+
+int fail(pcs_ctx *ctx, int status, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_tls_error = buf;
+    if (ctx) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->error = buf;
+    }
+    return status;
+}
+
+#define CU(ctx, call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ctx, PCS_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                    \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                          \
+    } while (0)
+
+bool is_identity3(const float *r) {
+    static const float I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int i = 0; i < 9; ++i)
+        if (r[i] != I[i]) return false;
+    return true;
+}
+
+// Choose the cheapest tex-coordinate path that is still bit-exact (pcs_device.cuh).
+int pick_tex_mode(const pcs_stream_desc &d) {
+    if (!is_identity3(d.d2c_rotation)) return TEX_GENERAL;
+    const bool t0 = d.d2c_translation[0] == 0.f && d.d2c_translation[1] == 0.f &&
+                    d.d2c_translation[2] == 0.f;
+    const bool same = d.depth.width == d.color.width && d.depth.height == d.color.height &&
+                      d.depth.fx == d.color.fx && d.depth.fy == d.color.fy &&
+                      d.depth.ppx == d.color.ppx && d.depth.ppy == d.color.ppy;
+    // the error bound behind TEX_ALIGNED (oracle/SPEC.md s1) needs ordinary magnitudes
+    const bool sane = d.depth.width <= 4096 && d.depth.height <= 4096 && d.depth.fx >= 16.f &&
+                      d.depth.fy >= 16.f && d.depth.fx <= 65536.f && d.depth.fy <= 65536.f &&
+                      d.depth.ppx >= 0.f && d.depth.ppx <= (float)d.depth.width &&
+                      d.depth.ppy >= 0.f && d.depth.ppy <= (float)d.depth.height &&
+                      d.depth_scale >= 1e-6f && d.depth_scale <= 1.0f;
+    if (t0 && same && sane) return TEX_ALIGNED;
+    return TEX_TRANSLATE;
+}
+
+void digest(const pcs_stream_desc &d, StreamParams &p) {
+    memset(&p, 0, sizeof p);
+    p.W = d.depth.width; p.H = d.depth.height; p.N = p.W * p.H;
+    p.CW = d.color.width; p.CH = d.color.height; p.bpp = d.color_bpp; p.stride = d.color_stride;
+    p.tex_mode = pick_tex_mode(d);
+    p.ppx = d.depth.ppx; p.ppy = d.depth.ppy; p.fx = d.depth.fx; p.fy = d.depth.fy;
+    p.cppx = d.color.ppx; p.cppy = d.color.ppy; p.cfx = d.color.fx; p.cfy = d.color.fy;
+    p.cwf = (float)d.color.width; p.chf = (float)d.color.height;
+    p.depth_scale = d.depth_scale;
+    memcpy(p.R, d.d2c_rotation, sizeof p.R);
+    memcpy(p.T, d.d2c_translation, sizeof p.T);
+    memcpy(p.tf, d.tf, sizeof p.tf);
+    p.cutoff = d.cutoff != 0; p.lane_rev = d.cutoff_lane_reversed != 0;
+    p.z_lo = d.z_lo; p.z_hi = d.z_hi; p.x_lo = d.x_lo; p.x_hi = d.x_hi;
+}
+
+int check_stream(pcs_ctx *ctx, int stream, bool need_depth) {
+    if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
+    if (stream < 0 || stream >= ctx->max_streams)
+        return fail(ctx, PCS_ERR_INVALID, "stream %d out of range [0,%d)", stream, ctx->max_streams);
+    StreamState &s = ctx->streams[stream];
+    if (!s.configured) return fail(ctx, PCS_ERR_INVALID, "stream %d not configured", stream);
+    if (need_depth && (s.params.W % 8 != 0 || s.params.N <= 0))
+        return fail(ctx, PCS_ERR_UNSUPPORTED, "depth width must be a positive multiple of 8");
+    return PCS_OK;
+}
+
+template <class T> int grow(pcs_ctx *ctx, T *&p, size_t count) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    if (cudaMalloc(&p, count * sizeof(T) + 64) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, PCS_ERR_NOMEM, "cudaMalloc of %zu bytes failed", count * sizeof(T));
+    }
+    return PCS_OK;
+}
+
+int ensure_frame_buffers(pcs_ctx *ctx, StreamState &s) {
+    const size_t n = (size_t)s.params.N, cb = (size_t)s.params.CH * s.params.stride;
+    int rc;
+    if (n > s.cap_pts) {
+        if ((rc = grow(ctx, s.d_z16, n))) return rc;
+        if ((rc = grow(ctx, s.d_payload, n * 5))) return rc;
+        if ((rc = grow(ctx, s.d_dense, n * 5))) return rc;
+        if ((rc = grow(ctx, s.d_keep, n))) return rc;
+        if ((rc = grow(ctx, s.d_tiles, n / CMP_TILE + 2))) return rc;
+        s.cap_pts = n;
+    }
+    if (cb > s.cap_color) {
+        if ((rc = grow(ctx, s.d_color, cb))) return rc;
+        s.cap_color = cb;
+    }
+    if (!s.d_count) {
+        CU(ctx, cudaMalloc(&s.d_count, 64));
+        CU(ctx, cudaHostAlloc(&s.h_count, 64, cudaHostAllocDefault));
+        CU(ctx, cudaMalloc(&s.d_job, sizeof(DevJob)));
+    }
+    return PCS_OK;
+}
+
+// -c: dense records + keep flags -> compacted payload, count to d_count.
+int launch_compaction(pcs_ctx *ctx, const uint8_t *keep, const int16_t *dense, int n, int lane_rev,
+                      int32_t *tiles, int16_t *out, int32_t *count, cudaStream_t cs) {
+    const int n_tiles = (n + CMP_TILE - 1) / CMP_TILE;
+    compact_count<<<n_tiles, CMP_THREADS, 0, cs>>>(keep, n, lane_rev, tiles);
+    compact_scan<<<1, 1024, 0, cs>>>(tiles, n_tiles, count, nullptr);
+    compact_scatter<<<n_tiles, CMP_THREADS, 0, cs>>>(keep, dense, n, lane_rev, tiles, out);
+    CU(ctx, cudaGetLastError());
+    return 3;
+}
+
+template <int MODE> void launch_k1_mode(bool cutoff, bool floatout, dim3 grid, cudaStream_t cs,
+                                        const DevJob *jobs, const StreamParams *params) {
+    if (cutoff) {
+        if (floatout) k1_direct<MODE, true, true><<<grid, K1_THREADS, 0, cs>>>(jobs, params);
+        else k1_direct<MODE, true, false><<<grid, K1_THREADS, 0, cs>>>(jobs, params);
+    } else {
+        if (floatout) k1_direct<MODE, false, true><<<grid, K1_THREADS, 0, cs>>>(jobs, params);
+        else k1_direct<MODE, false, false><<<grid, K1_THREADS, 0, cs>>>(jobs, params);
+    }
+}
+
+void launch_k1_direct(int tex_mode, bool cutoff, bool floatout, dim3 grid, cudaStream_t cs,
+                      const DevJob *jobs, const StreamParams *params) {
+    switch (tex_mode) {
+        case TEX_ALIGNED: launch_k1_mode<TEX_ALIGNED>(cutoff, floatout, grid, cs, jobs, params); break;
+        case TEX_TRANSLATE: launch_k1_mode<TEX_TRANSLATE>(cutoff, floatout, grid, cs, jobs, params); break;
+        default: launch_k1_mode<TEX_GENERAL>(cutoff, floatout, grid, cs, jobs, params); break;
+    }
+}
+
+int tiles_for(int n_pts) { return (n_pts / 8 + K1_THREADS - 1) / K1_THREADS; }
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int pcs_b200_abi_version(void) { return PCS_B200_ABI_VERSION; }
+
+const char *pcs_b200_status_string(int status) {
+    switch (status) {
+        case PCS_OK: return "ok";
+        case PCS_ERR_INVALID: return "invalid argument";
+        case PCS_ERR_CUDA: return "CUDA error";
+        case PCS_ERR_NOMEM: return "out of memory";
+        case PCS_ERR_UNSUPPORTED: return "unsupported";
+        case PCS_ERR_CAPACITY: return "output buffer too small";
+        default: return status >= 0 ? "ok" : "unknown error";
+    }
+}
+
+const char *pcs_b200_last_error(const pcs_ctx *ctx) {
+    return ctx ? ctx->error.c_str() : g_tls_error.c_str();
+}
+
+int pcs_b200_create(const pcs_config *cfg, pcs_ctx **out) {
+    if (!cfg || !out) return fail(nullptr, PCS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->max_streams < 1 || cfg->max_streams > 4096)
+        return fail(nullptr, PCS_ERR_INVALID, "max_streams must be in [1,4096]");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, PCS_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(nullptr, PCS_ERR_INVALID, "device %d out of range", cfg->device);
+    CU(nullptr, cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(nullptr, PCS_ERR_UNSUPPORTED, "built for sm_100a only; device is sm_%d%d",
+                    prop.major, prop.minor);
+    pcs_ctx *ctx = new pcs_ctx;
+    ctx->device = cfg->device;
+    ctx->max_streams = cfg->max_streams;
+    ctx->kernel_variant = cfg->kernel_variant;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->streams = new StreamState[cfg->max_streams];
+    if (cudaMalloc(&ctx->d_params, sizeof(StreamParams) * cfg->max_streams) != cudaSuccess) {
+        pcs_b200_destroy(ctx);
+        return fail(nullptr, PCS_ERR_NOMEM, "cudaMalloc failed");
+    }
+    for (int i = 0; i < cfg->max_streams; ++i)
+        if (cudaStreamCreateWithFlags(&ctx->streams[i].cs, cudaStreamNonBlocking) != cudaSuccess) {
+            pcs_b200_destroy(ctx);
+            return fail(nullptr, PCS_ERR_CUDA, "cudaStreamCreate failed");
+        }
+    int rc = pipe_configure(ctx->sm_count);
+    if (rc != PCS_OK) {
+        pcs_b200_destroy(ctx);
+        return fail(nullptr, PCS_ERR_CUDA, "kernel attribute setup failed: %s",
+                    cudaGetErrorString(cudaGetLastError()));
+    }
+    *out = ctx;
+    return PCS_OK;
+}
+
+void pcs_b200_destroy(pcs_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; ctx->streams && i < ctx->max_streams; ++i) {
+        StreamState &s = ctx->streams[i];
+        if (s.cs) { cudaStreamSynchronize(s.cs); cudaStreamDestroy(s.cs); }
+        cudaFree(s.d_z16); cudaFree(s.d_color); cudaFree(s.d_payload); cudaFree(s.d_dense);
+        cudaFree(s.d_keep); cudaFree(s.d_tiles); cudaFree(s.d_count); cudaFree(s.d_job);
+        cudaFree(s.d_xyz); cudaFree(s.d_uv); cudaFree(s.d_vpayload);
+        cudaFree(s.d_cdense); cudaFree(s.d_ckeep); cudaFree(s.d_ctiles);
+        if (s.h_count) cudaFreeHost(s.h_count);
+    }
+    delete[] ctx->streams;
+    cudaFree(ctx->d_params);
+    cudaFree(ctx->d_stitch_in);
+    cudaFree(ctx->d_stitch_out);
+    voxel_free(ctx->voxel);
+    delete ctx;
+}
+
+int pcs_b200_set_stream(pcs_ctx *ctx, int stream, const pcs_stream_desc *desc) {
+    if (!ctx || !desc) return fail(ctx, PCS_ERR_INVALID, "null argument");
+    if (stream < 0 || stream >= ctx->max_streams)
+        return fail(ctx, PCS_ERR_INVALID, "stream %d out of range [0,%d)", stream, ctx->max_streams);
+    const pcs_stream_desc &d = *desc;
+    if (d.color.width < 1 || d.color.height < 1 || d.color_bpp < 3 ||
+        d.color_stride < d.color.width * d.color_bpp)
+        return fail(ctx, PCS_ERR_INVALID, "bad colour geometry (bpp >= 3, stride >= width*bpp)");
+    if (d.depth.width < 0 || d.depth.height < 0 ||
+        (long long)d.depth.width * d.depth.height > (1ll << 28))
+        return fail(ctx, PCS_ERR_INVALID, "bad depth geometry");
+    CU(ctx, cudaSetDevice(ctx->device));
+    StreamState &s = ctx->streams[stream];
+    std::lock_guard<std::mutex> lk(s.mu);
+    s.desc = d;
+    digest(d, s.params);
+    s.configured = true;
+    CU(ctx, cudaMemcpy(ctx->d_params + stream, &s.params, sizeof(StreamParams), cudaMemcpyHostToDevice));
+    return PCS_OK;
+}
+
+void *pcs_b200_host_alloc(pcs_ctx *ctx, size_t bytes) {
+    void *p = nullptr;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        fail(ctx, PCS_ERR_NOMEM, "cudaHostAlloc of %zu bytes failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void pcs_b200_host_free(pcs_ctx *ctx, void *p) {
+    if (ctx) cudaSetDevice(ctx->device);
+    if (p) cudaFreeHost(p);
+}
+
+int pcs_b200_synchronize(pcs_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize((cudaStream_t)cuda_stream));
+    return PCS_OK;
+}
+
+// ---- camera side, host buffers ---------------------------------------------
+int pcs_b200_send_xyzrgb_begin(pcs_ctx *ctx, int stream, const uint16_t *z16_host,
+                               const uint8_t *color_host, int16_t *buffer_host, int write_header) {
+    int rc = check_stream(ctx, stream, true);
+    if (rc) return rc;
+    if (!z16_host || !color_host || !buffer_host) return fail(ctx, PCS_ERR_INVALID, "null buffer");
+    StreamState &s = ctx->streams[stream];
+    std::lock_guard<std::mutex> lk(s.mu);
+    if (s.pending) return fail(ctx, PCS_ERR_INVALID, "stream %d already has a frame in flight", stream);
+    const StreamParams &p = s.params;
+    if ((size_t)p.N * 10 + 4 > (size_t)PCS_B200_CAMERA_BUF_SHORTS * 2)
+        return fail(ctx, PCS_ERR_CAPACITY, "%d points do not fit the reference's 10 MB camera buffer", p.N);
+    CU(ctx, cudaSetDevice(ctx->device));
+    if ((rc = ensure_frame_buffers(ctx, s))) return rc;
+    DevJob job{};
+    job.z16 = s.d_z16; job.color = s.d_color; job.payload = s.d_payload; job.xyzrgb = nullptr;
+    job.count = s.d_count; job.keep = s.d_keep; job.dense = s.d_dense; job.stream = stream;
+    CU(ctx, cudaMemcpyAsync(s.d_job, &job, sizeof job, cudaMemcpyHostToDevice, s.cs));
+    CU(ctx, cudaMemcpyAsync(s.d_z16, z16_host, (size_t)p.N * 2, cudaMemcpyHostToDevice, s.cs));
+    CU(ctx, cudaMemcpyAsync(s.d_color, color_host, (size_t)p.CH * p.stride, cudaMemcpyHostToDevice, s.cs));
+    dim3 grid(tiles_for(p.N), 1);
+    launch_k1_direct(p.tex_mode, p.cutoff, false, grid, s.cs, s.d_job, ctx->d_params);
+    CU(ctx, cudaGetLastError());
+    uint8_t *dst = reinterpret_cast<uint8_t *>(buffer_host) + PCS_B200_HEADER_BYTES;
+    if (p.cutoff) {
+        rc = launch_compaction(ctx, s.d_keep, s.d_dense, p.N, p.lane_rev, s.d_tiles, s.d_payload,
+                               s.d_count, s.cs);
+        if (rc < 0) return rc;
+        CU(ctx, cudaMemcpyAsync(s.h_count, s.d_count, 4, cudaMemcpyDeviceToHost, s.cs));
+        // the count is only known on the device: copy the whole frame's worth, trim in end()
+    }
+    CU(ctx, cudaMemcpyAsync(dst, s.d_payload, (size_t)p.N * 10, cudaMemcpyDeviceToHost, s.cs));
+    s.pending = true;
+    s.pending_buffer = buffer_host;
+    s.pending_header = write_header;
+    return PCS_OK;
+}
+
+int pcs_b200_send_xyzrgb_end(pcs_ctx *ctx, int stream) {
+    int rc = check_stream(ctx, stream, true);
+    if (rc) return rc;
+    StreamState &s = ctx->streams[stream];
+    std::lock_guard<std::mutex> lk(s.mu);
+    if (!s.pending) return fail(ctx, PCS_ERR_INVALID, "stream %d has no frame in flight", stream);
+    s.pending = false;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(s.cs));
+    const StreamParams &p = s.params;
+    const int count = p.cutoff ? *s.h_count : p.N;
+    const int size = 5 * count * (int)sizeof(int16_t);              // :697
+    uint8_t *b = reinterpret_cast<uint8_t *>(s.pending_buffer);
+    // :673 memset(buffer, 0, BUF_SIZE) happens before packing: whatever the pack did not
+    // overwrite inside the first 5 000 000 bytes is zero afterwards.
+    const size_t zero_end = PCS_B200_CAMERA_BUF_SHORTS;             // bytes
+    const size_t used_end = PCS_B200_HEADER_BYTES + (size_t)size;
+    if (used_end < zero_end) {
+        // with cutoff the D2H copied N records; everything past `count` is scratch, not output
+        const size_t copied_end = PCS_B200_HEADER_BYTES + (size_t)p.N * 10;
+        memset(b + used_end, 0, zero_end - used_end);
+        (void)copied_end;
+    }
+    memset(b, 0, PCS_B200_HEADER_BYTES);
+    if (s.pending_header) memcpy(b, &size, sizeof(int));            // :715-718
+    return size;
+}
+
+int pcs_b200_send_xyzrgb(pcs_ctx *ctx, int stream, const uint16_t *z16_host,
+                         const uint8_t *color_host, int16_t *buffer_host, int write_header) {
+    int rc = pcs_b200_send_xyzrgb_begin(ctx, stream, z16_host, color_host, buffer_host, write_header);
+    if (rc) return rc;
+    return pcs_b200_send_xyzrgb_end(ctx, stream);
+}
+
+int pcs_b200_pack_from_vertices_dev(pcs_ctx *ctx, int stream, const float *xyz_dev,
+                                    const float *uv_dev, int n, const uint8_t *color_dev,
+                                    int16_t *payload_dev, int32_t *count_dev, void *cuda_stream) {
+    int rc = check_stream(ctx, stream, false);
+    if (rc) return rc;
+    if (n < 0 || (n & 3)) return fail(ctx, PCS_ERR_INVALID, "n must be a non-negative multiple of 4");
+    if (n == 0) return 0;
+    if (!xyz_dev || !uv_dev || !color_dev || !payload_dev) return fail(ctx, PCS_ERR_INVALID, "null buffer");
+    if (reinterpret_cast<uintptr_t>(color_dev) & 3)
+        return fail(ctx, PCS_ERR_INVALID, "colour frame must be 4-byte aligned");
+    StreamState &s = ctx->streams[stream];
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int blocks = (n + 255) / 256;
+    if (!s.params.cutoff) {
+        k1a_vertices<false><<<blocks, 256, 0, cs>>>(xyz_dev, uv_dev, n, color_dev, ctx->d_params,
+                                                    stream, payload_dev, nullptr);
+        CU(ctx, cudaGetLastError());
+        return n;
+    }
+    // -c needs scratch: ctx-owned, sized for n
+    std::lock_guard<std::mutex> lk(s.mu);
+    if ((size_t)n > s.cap_cut) {
+        if ((rc = grow(ctx, s.d_cdense, (size_t)n * 5))) return rc;
+        if ((rc = grow(ctx, s.d_ckeep, (size_t)n))) return rc;
+        if ((rc = grow(ctx, s.d_ctiles, (size_t)n / CMP_TILE + 2))) return rc;
+        s.cap_cut = n;
+    }
+    if (!count_dev) {
+        if (!s.d_count) {
+            CU(ctx, cudaMalloc(&s.d_count, 64));
+            CU(ctx, cudaHostAlloc(&s.h_count, 64, cudaHostAllocDefault));
+            CU(ctx, cudaMalloc(&s.d_job, sizeof(DevJob)));
+        }
+        count_dev = s.d_count;
+    }
+    k1a_vertices<true><<<blocks, 256, 0, cs>>>(xyz_dev, uv_dev, n, color_dev, ctx->d_params, stream,
+                                               s.d_cdense, s.d_ckeep);
+    CU(ctx, cudaGetLastError());
+    rc = launch_compaction(ctx, s.d_ckeep, s.d_cdense, n, s.params.lane_rev, s.d_ctiles, payload_dev,
+                           count_dev, cs);
+    if (rc < 0) return rc;
+    return n;  // upper bound; the exact count is in *count_dev
+}
+
+int pcs_b200_pack_from_vertices(pcs_ctx *ctx, int stream, const float *xyz_host,
+                                const float *uv_host, int n, const uint8_t *color_host,
+                                int16_t *payload_host) {
+    int rc = check_stream(ctx, stream, false);
+    if (rc) return rc;
+    if (n < 0 || (n & 3)) return fail(ctx, PCS_ERR_INVALID, "n must be a non-negative multiple of 4");
+    if (n == 0) return 0;
+    if (!xyz_host || !uv_host || !color_host || !payload_host) return fail(ctx, PCS_ERR_INVALID, "null buffer");
+    StreamState &s = ctx->streams[stream];
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t cb = (size_t)s.params.CH * s.params.stride;
+    {
+        std::lock_guard<std::mutex> lk(s.mu);
+        if ((size_t)n > s.cap_vtx) {
+            if ((rc = grow(ctx, s.d_xyz, (size_t)n * 3))) return rc;
+            if ((rc = grow(ctx, s.d_uv, (size_t)n * 2))) return rc;
+            if ((rc = grow(ctx, s.d_vpayload, (size_t)n * 5))) return rc;
+            s.cap_vtx = n;
+        }
+        if (cb > s.cap_color) {
+            if ((rc = grow(ctx, s.d_color, cb))) return rc;
+            s.cap_color = cb;
+        }
+        if (!s.d_count) {
+            CU(ctx, cudaMalloc(&s.d_count, 64));
+            CU(ctx, cudaHostAlloc(&s.h_count, 64, cudaHostAllocDefault));
+            CU(ctx, cudaMalloc(&s.d_job, sizeof(DevJob)));
+        }
+    }
+    CU(ctx, cudaMemcpyAsync(s.d_xyz, xyz_host, (size_t)n * 12, cudaMemcpyHostToDevice, s.cs));
+    CU(ctx, cudaMemcpyAsync(s.d_uv, uv_host, (size_t)n * 8, cudaMemcpyHostToDevice, s.cs));
+    CU(ctx, cudaMemcpyAsync(s.d_color, color_host, cb, cudaMemcpyHostToDevice, s.cs));
+    rc = pcs_b200_pack_from_vertices_dev(ctx, stream, s.d_xyz, s.d_uv, n, s.d_color, s.d_vpayload,
+                                         s.d_count, s.cs);
+    if (rc < 0) return rc;
+    int count = n;
+    if (s.params.cutoff) {
+        CU(ctx, cudaMemcpyAsync(s.h_count, s.d_count, 4, cudaMemcpyDeviceToHost, s.cs));
+        CU(ctx, cudaStreamSynchronize(s.cs));
+        count = *s.h_count;
+    }
+    CU(ctx, cudaMemcpyAsync(payload_host, s.d_vpayload, (size_t)count * 10, cudaMemcpyDeviceToHost, s.cs));
+    CU(ctx, cudaStreamSynchronize(s.cs));
+    return count;
+}
+
+// ---- camera side, batched ----------------------------------------------------
+int pcs_b200_batch_create(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs, pcs_batch **out) {
+    if (!ctx || !jobs || !out || n_jobs < 1 || n_jobs > 65535)
+        return fail(ctx, PCS_ERR_INVALID, "bad batch arguments (1 <= n_jobs <= 65535)");
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    pcs_batch *b = new pcs_batch;
+    auto bail = [&](int rc) { pcs_b200_batch_destroy(ctx, b); return rc; };
+    // order jobs by kernel variant so that each variant is one launch
+    std::vector<int> order;
+    for (int v = 0; v < 12; ++v) {
+        const int tm = v % 3, cut = (v / 3) & 1, fo = v / 6;
+        pcs_batch::Group g{tm, cut, fo, (int)order.size(), 0, 0, 0};
+        for (int j = 0; j < n_jobs; ++j) {
+            int rc = check_stream(ctx, jobs[j].stream, true);
+            if (rc) return bail(rc);
+            const StreamParams &p = ctx->streams[jobs[j].stream].params;
+            if (p.tex_mode == tm && p.cutoff == cut && (jobs[j].xyzrgb_dev != nullptr) == (fo != 0)) {
+                order.push_back(j);
+                g.count++;
+                g.max_tiles = std::max(g.max_tiles, tiles_for(p.N));
+                g.max_octets = std::max(g.max_octets, p.N / 8);
+            }
+        }
+        if (g.count) b->groups.push_back(g);
+    }
+    for (int j : order) {
+        const pcs_frame_job &in = jobs[j];
+        const StreamParams &p = ctx->streams[in.stream].params;
+        if (!in.z16_dev || !in.color_dev || !in.payload_dev) return bail(fail(ctx, PCS_ERR_INVALID, "job %d: null buffer", j));
+        if ((reinterpret_cast<uintptr_t>(in.z16_dev) & 15) || (reinterpret_cast<uintptr_t>(in.color_dev) & 15))
+            return bail(fail(ctx, PCS_ERR_INVALID, "job %d: frames must be 16-byte aligned", j));
+        if (in.xyzrgb_dev && (reinterpret_cast<uintptr_t>(in.xyzrgb_dev) & 15))
+            return bail(fail(ctx, PCS_ERR_INVALID, "job %d: xyzrgb must be 16-byte aligned", j));
+        DevJob d{};
+        d.z16 = in.z16_dev; d.color = in.color_dev; d.payload = in.payload_dev;
+        d.xyzrgb = in.xyzrgb_dev; d.count = in.count_dev; d.stream = in.stream;
+        if (p.cutoff) {
+            void *dense = nullptr, *keep = nullptr, *tiles = nullptr;
+            const int n_tiles = (p.N + CMP_TILE - 1) / CMP_TILE;
+            if (cudaMalloc(&dense, (size_t)p.N * 10 + 64) != cudaSuccess ||
+                cudaMalloc(&keep, (size_t)p.N + 64) != cudaSuccess ||
+                cudaMalloc(&tiles, (size_t)(n_tiles + 2) * 4) != cudaSuccess) {
+                cudaGetLastError();
+                cudaFree(dense); cudaFree(keep); cudaFree(tiles);
+                return bail(fail(ctx, PCS_ERR_NOMEM, "cutoff scratch allocation failed"));
+            }
+            b->owned.push_back(dense); b->owned.push_back(keep); b->owned.push_back(tiles);
+            d.dense = (int16_t *)dense; d.keep = (uint8_t *)keep;
+            b->cuts.push_back({(int)b->jobs.size(), p.N, p.lane_rev, n_tiles, (int32_t *)tiles});
+        }
+        b->jobs.push_back(d);
+    }
+    if (cudaMalloc(&b->d_jobs, sizeof(DevJob) * b->jobs.size()) != cudaSuccess) {
+        cudaGetLastError();
+        return bail(fail(ctx, PCS_ERR_NOMEM, "job table allocation failed"));
+    }
+    if (cudaMemcpy(b->d_jobs, b->jobs.data(), sizeof(DevJob) * b->jobs.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(fail(ctx, PCS_ERR_CUDA, "job table upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+    // pipelined variant: every job must be plain (no cutoff, no float output) and 16-B aligned
+    b->use_pipe = false;
+    if (ctx->kernel_variant != 1) {
+        bool ok = true;
+        for (size_t i = 0; i < b->jobs.size(); ++i) {
+            const StreamParams &p = ctx->streams[b->jobs[i].stream].params;
+            ok = ok && pipe_supports(p) && !b->jobs[i].xyzrgb &&
+                 !(reinterpret_cast<uintptr_t>(b->jobs[i].payload) & 15);
+        }
+        if (ok) {
+            std::vector<StreamParams> sp(ctx->max_streams);
+            for (int i = 0; i < ctx->max_streams; ++i) sp[i] = ctx->streams[i].params;
+            int rc = pipe_build(b->pipe, b->jobs, sp, ctx->sm_count);
+            if (rc == PCS_OK) b->use_pipe = true;
+            else if (ctx->kernel_variant == 2)
+                return bail(fail(ctx, rc, "pipelined kernel setup failed"));
+        } else if (ctx->kernel_variant == 2) {
+            return bail(fail(ctx, PCS_ERR_UNSUPPORTED,
+                             "kernel_variant=2 needs plain jobs (no cutoff / float output, aligned payloads)"));
+        }
+    }
+    b->launches = b->use_pipe ? pipe_launches(b->pipe) : (int)b->groups.size() + 3 * (int)b->cuts.size();
+    *out = b;
+    return PCS_OK;
+}
+
+int pcs_b200_batch_run(pcs_ctx *ctx, pcs_batch *b, void *cuda_stream) {
+    if (!ctx || !b) return fail(ctx, PCS_ERR_INVALID, "null argument");
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (b->use_pipe) {
+        pipe_launch(b->pipe, b->d_jobs, ctx->d_params, cs);
+        CU(ctx, cudaGetLastError());
+        return PCS_OK;
+    }
+    for (const auto &g : b->groups) {
+        dim3 grid(g.max_tiles, g.count);
+        launch_k1_direct(g.tex_mode, g.cutoff != 0, g.floatout != 0, grid, cs, b->d_jobs + g.first,
+                         ctx->d_params);
+    }
+    CU(ctx, cudaGetLastError());
+    for (const auto &c : b->cuts) {
+        const DevJob &j = b->jobs[c.job];
+        int rc = launch_compaction(ctx, j.keep, j.dense, c.n, c.lane_rev, c.d_tiles, j.payload, j.count, cs);
+        if (rc < 0) return rc;
+    }
+    return PCS_OK;
+}
+
+int pcs_b200_batch_launches(const pcs_batch *b) { return b ? b->launches : 0; }
+
+void pcs_b200_batch_destroy(pcs_ctx *ctx, pcs_batch *b) {
+    if (!b) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    for (void *p : b->owned) cudaFree(p);
+    cudaFree(b->d_jobs);
+    pipe_free(b->pipe);
+    delete b;
+}
+
+// ---- stitch side ---------------------------------------------------------------
+static int stitch_common(pcs_ctx *ctx, const int16_t *const *payload_dev, const int32_t *n_shorts,
+                         int n_cams, int downsample, const float *transforms, bool pcl,
+                         uint8_t *stitched_dev, size_t cap, void *cloud32_dev, cudaStream_t cs) {
+    if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
+    if (!payload_dev || !n_shorts || !stitched_dev || n_cams < 0 || downsample < 1 || (pcl && !transforms))
+        return fail(ctx, PCS_ERR_INVALID, "bad stitch arguments");
+    if (n_cams > MAX_CAMS) return fail(ctx, PCS_ERR_UNSUPPORTED, "at most %d cameras per call", MAX_CAMS);
+    if (reinterpret_cast<uintptr_t>(stitched_dev) & 3)
+        return fail(ctx, PCS_ERR_INVALID, "stitched buffer must be 4-byte aligned");
+    CamTable tab{};
+    TfTable tfs{};
+    tab.n_cams = n_cams;
+    tab.downsample = downsample;
+    long long total = 0;
+    for (int i = 0; i < n_cams; ++i) {
+        if (n_shorts[i] < 0 || (n_shorts[i] && !payload_dev[i])) return fail(ctx, PCS_ERR_INVALID, "camera %d: bad payload", i);
+        const int n_in = n_shorts[i] / 5;
+        // raw: for (j = 0; j < n_shorts; j += 5*ds)  -> ceil(n_shorts / (5*ds)) records
+        //      (src/pcs-multicamera-client.cpp:388); a trailing partial record is read as the
+        //      reference would, so n_shorts must be a multiple of 5 here.
+        // pcl: width = size / ds (src/pcs-multicamera-optimized.cpp:230)
+        if (n_shorts[i] % 5) return fail(ctx, PCS_ERR_INVALID, "camera %d: payload is not whole records", i);
+        const int n_out = pcl ? n_in / downsample : (n_in + downsample - 1) / downsample;
+        tab.src[i] = payload_dev[i];
+        tab.n_in[i] = n_in;
+        tab.out_off[i] = (int)total;
+        total += n_out;
+        if (pcl) memcpy(tfs.m[i], transforms + 16 * i, 12 * sizeof(float));
+    }
+    if (total * 10 > 0x7fffffffll) return fail(ctx, PCS_ERR_CAPACITY, "stitched payload exceeds int32");
+    tab.out_off[n_cams] = (int)total;
+    if ((size_t)total * 10 + 4 > cap) return fail(ctx, PCS_ERR_CAPACITY, "stitched buffer too small: need %lld bytes", total * 10 + 4);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int blocks = std::max(1, (int)((total + 255) / 256));
+    if (pcl) stitch_kernel<true><<<blocks, 256, 0, cs>>>(tab, tfs, stitched_dev, (float4 *)cloud32_dev);
+    else stitch_kernel<false><<<blocks, 256, 0, cs>>>(tab, tfs, stitched_dev, nullptr);
+    CU(ctx, cudaGetLastError());
+    return (int)(total * 10);
+}
+
+int pcs_b200_stitch_raw_dev(pcs_ctx *ctx, const int16_t *const *payload_dev, const int32_t *n_shorts,
+                            int n_cams, int downsample, uint8_t *stitched_dev, size_t stitched_cap,
+                            void *cuda_stream) {
+    return stitch_common(ctx, payload_dev, n_shorts, n_cams, downsample, nullptr, false, stitched_dev,
+                         stitched_cap, nullptr, (cudaStream_t)cuda_stream);
+}
+
+int pcs_b200_stitch_pcl_dev(pcs_ctx *ctx, const int16_t *const *payload_dev, const int32_t *n_shorts,
+                            int n_cams, int downsample, const float *transforms,
+                            uint8_t *stitched_dev, size_t stitched_cap, void *cloud32_dev,
+                            void *cuda_stream) {
+    if (cloud32_dev && (reinterpret_cast<uintptr_t>(cloud32_dev) & 15))
+        return fail(ctx, PCS_ERR_INVALID, "cloud32 must be 16-byte aligned");
+    return stitch_common(ctx, payload_dev, n_shorts, n_cams, downsample, transforms, true, stitched_dev,
+                         stitched_cap, cloud32_dev, (cudaStream_t)cuda_stream);
+}
+
+static int stitch_host(pcs_ctx *ctx, const int16_t *const *payload_host, const int32_t *n_shorts,
+                       int n_cams, int downsample, const float *transforms, bool pcl,
+                       uint8_t *stitched_host, size_t cap) {
+    if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
+    if (!payload_host || !n_shorts || !stitched_host || n_cams < 0 || n_cams > MAX_CAMS)
+        return fail(ctx, PCS_ERR_INVALID, "bad stitch arguments");
+    CU(ctx, cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->scratch_mu);
+    size_t in_bytes = 0;
+    std::vector<size_t> off(n_cams);
+    for (int i = 0; i < n_cams; ++i) {
+        if (n_shorts[i] < 0) return fail(ctx, PCS_ERR_INVALID, "negative payload length");
+        off[i] = in_bytes;
+        in_bytes += ((size_t)n_shorts[i] * 2 + 15) & ~(size_t)15;
+    }
+    const size_t out_bytes = in_bytes + 64;
+    if (in_bytes + 64 > ctx->cap_stitch_in) {
+        cudaFree(ctx->d_stitch_in);
+        ctx->d_stitch_in = nullptr; ctx->cap_stitch_in = 0;
+        if (cudaMalloc(&ctx->d_stitch_in, in_bytes + 64) != cudaSuccess) { cudaGetLastError(); return fail(ctx, PCS_ERR_NOMEM, "cudaMalloc failed"); }
+        ctx->cap_stitch_in = in_bytes + 64;
+    }
+    if (out_bytes > ctx->cap_stitch_out) {
+        cudaFree(ctx->d_stitch_out);
+        ctx->d_stitch_out = nullptr; ctx->cap_stitch_out = 0;
+        if (cudaMalloc(&ctx->d_stitch_out, out_bytes) != cudaSuccess) { cudaGetLastError(); return fail(ctx, PCS_ERR_NOMEM, "cudaMalloc failed"); }
+        ctx->cap_stitch_out = out_bytes;
+    }
+    cudaStream_t cs = ctx->streams[0].cs;
+    std::vector<const int16_t *> dev(n_cams);
+    for (int i = 0; i < n_cams; ++i) {
+        dev[i] = reinterpret_cast<const int16_t *>(ctx->d_stitch_in + off[i]);
+        if (n_shorts[i])
+            if (cudaMemcpyAsync(ctx->d_stitch_in + off[i], payload_host[i], (size_t)n_shorts[i] * 2, cudaMemcpyHostToDevice, cs) != cudaSuccess)
+                return fail(ctx, PCS_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    // records at +16 so that they are 16-byte aligned: the [int32] header sits at +12
+    uint8_t *st = ctx->d_stitch_out + 12;
+    int size = stitch_common(ctx, dev.data(), n_shorts, n_cams, downsample, transforms, pcl, st,
+                             std::min(cap, ctx->cap_stitch_out - 12), nullptr, cs);
+    if (size < 0) return size;
+    if (cudaMemcpyAsync(stitched_host, st, (size_t)size + 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
+        cudaStreamSynchronize(cs) != cudaSuccess)
+        return fail(ctx, PCS_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return size;
+}
+
+int pcs_b200_stitch_raw(pcs_ctx *ctx, const int16_t *const *payload_host, const int32_t *n_shorts,
+                        int n_cams, int downsample, uint8_t *stitched_host, size_t stitched_cap) {
+    return stitch_host(ctx, payload_host, n_shorts, n_cams, downsample, nullptr, false, stitched_host, stitched_cap);
+}
+
+int pcs_b200_stitch_pcl(pcs_ctx *ctx, const int16_t *const *payload_host, const int32_t *n_shorts,
+                        int n_cams, int downsample, const float *transforms,
+                        uint8_t *stitched_host, size_t stitched_cap) {
+    if (!transforms) return fail(ctx, PCS_ERR_INVALID, "null transforms");
+    return stitch_host(ctx, payload_host, n_shorts, n_cams, downsample, transforms, true, stitched_host, stitched_cap);
+}
+
+// ---- voxel merge -----------------------------------------------------------------
+int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
+                             int16_t *out_dev, void *cuda_stream) {
+    if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
+    if (n < 0 || leaf_mm < 1 || leaf_mm > 32767 || (n && (!records_dev || !out_dev)))
+        return fail(ctx, PCS_ERR_INVALID, "bad voxel-merge arguments");
+    if (n == 0) return 0;
+    CU(ctx, cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->scratch_mu);
+    int rc = voxel_merge(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream);
+    if (rc < 0)
+        return fail(ctx, rc == -3 ? PCS_ERR_NOMEM : (rc == -4 ? PCS_ERR_UNSUPPORTED : PCS_ERR_CUDA),
+                    "voxel merge failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
+
+int pcs_b200_voxel_merge(pcs_ctx *ctx, const int16_t *records_host, int n, int leaf_mm,
+                         int16_t *out_host) {
+    if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
+    if (n < 0 || (n && (!records_host || !out_host))) return fail(ctx, PCS_ERR_INVALID, "bad arguments");
+    if (n == 0) return 0;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int16_t *d_in = nullptr, *d_out = nullptr;
+    if (cudaMalloc(&d_in, (size_t)n * 10 + 64) != cudaSuccess || cudaMalloc(&d_out, (size_t)n * 10 + 64) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(d_in); cudaFree(d_out);
+        return fail(ctx, PCS_ERR_NOMEM, "cudaMalloc failed");
+    }
+    cudaStream_t cs = ctx->streams[0].cs;
+    int rc = PCS_ERR_CUDA;
+    if (cudaMemcpyAsync(d_in, records_host, (size_t)n * 10, cudaMemcpyHostToDevice, cs) == cudaSuccess) {
+        rc = pcs_b200_voxel_merge_dev(ctx, d_in, n, leaf_mm, d_out, cs);
+        if (rc > 0 && (cudaMemcpyAsync(out_host, d_out, (size_t)rc * 10, cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
+                       cudaStreamSynchronize(cs) != cudaSuccess))
+            rc = fail(ctx, PCS_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaFree(d_in); cudaFree(d_out);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,331 @@
+// Kernels of the hot path, "direct" variants (register loads, shared-memory
+// transposed stores).  The bulk-async pipelined K1 lives in pcs_k1_pipe.cuh.
+//
+//   k1_direct        z16 + RGB8 -> records      (rs2::pointcloud::calculate +
+//                                                copyPointCloudXYZRGBToBufferSIMD,
+//                                                src/pcs-camera-optimized.cpp:288,363-616)
+//   k1a_vertices     vertex/texcoord -> records (copyPointCloudXYZRGBToBufferSIMD itself)
+//   compact_*        order-preserving -c compaction (src/pcs-camera-optimized.cpp:499-577)
+//   stitch_raw       concat + stride decimation (src/pcs-multicamera-client.cpp:385-395)
+//   stitch_pcl       unpack + transform + append + repack
+//                                               (src/pcs-multicamera-optimized.cpp:226-265,289,366)
+#pragma once
+#include "pcs_device.cuh"
+
+namespace pcs {
+
+constexpr int K1_THREADS = 256;          // one octet (8 pixels) per thread
+constexpr int K1_TILE_PTS = K1_THREADS * 8;
+constexpr int MAX_CAMS = 32;
+
+struct DevJob {
+    const uint16_t *z16;
+    const uint8_t *color;
+    int16_t *payload;
+    float *xyzrgb;     // optional 16 B/pt output
+    int32_t *count;    // optional record count
+    uint8_t *keep;     // cutoff: per-point keep flags (scratch)
+    int16_t *dense;    // cutoff: uncompacted records (scratch); payload receives the compaction
+    int32_t stream;
+    int32_t pad;
+};
+
+// ---------------------------------------------------------------------------
+// Per-warp staging: 32 lanes x 80 B of records are written to shared memory at
+// lane*80 (16-byte STS, conflict-free: the eight lanes of a quarter-warp land on
+// 8 distinct 4-bank groups) and streamed out as 160 coalesced 16-byte stores.
+__device__ __forceinline__ void warp_store_records(uint4 *slab, const uint32_t (&w)[20], int lane,
+                                                   uint8_t *dst, int valid_octets, bool aligned) {
+    uint4 *mine = slab + lane * 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) mine[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    __syncwarp();
+    const int n16 = valid_octets * 5;  // 16-byte chunks owned by this warp
+    if (aligned) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int c = k * 32 + lane;
+            if (c < n16) st_global_v4(dst + (size_t)c * 16, slab[c]);
+        }
+    } else {  // payload not 16-byte aligned: 2-byte stores (always legal for a short*)
+        const uint16_t *s16 = reinterpret_cast<const uint16_t *>(slab);
+        uint16_t *d16 = reinterpret_cast<uint16_t *>(dst);
+        for (int c = lane; c < n16 * 8; c += 32) d16[c] = s16[c];
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// K1 direct: grid = (tiles per frame, jobs).
+template <int MODE, bool CUTOFF, bool FLOATOUT>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_direct(const DevJob *__restrict__ jobs, const StreamParams *__restrict__ streams) {
+    __shared__ uint4 slabs[K1_THREADS / 32][32 * 5];
+    __shared__ StreamParams sp;
+    const DevJob job = jobs[blockIdx.y];
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(streams + job.stream);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&sp);
+        for (int i = threadIdx.x; i < (int)(sizeof(StreamParams) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int octets = sp.N >> 3;
+    const int tile0 = blockIdx.x * K1_THREADS;  // first octet of this block
+    if (tile0 >= octets) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int o = tile0 + threadIdx.x;
+    const bool active = o < octets;
+    uint32_t w[20];
+    if (active) {
+        const int p0i = o * 8;
+        const int y = p0i / sp.W, x0 = p0i - y * sp.W;
+        const uint4 d = ld_global_nc_v4(job.z16 + p0i);
+        const uint32_t dz[4] = {d.x, d.y, d.z, d.w};
+        const float ny = __fdiv_rn(__fsub_rn((float)y, sp.ppy), sp.fy);
+        Rec rec[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t z16 = (k & 1) ? (dz[k >> 1] >> 16) : (dz[k >> 1] & 0xFFFFu);
+            const int x = x0 + k;
+            const float nx = __fdiv_rn(__fsub_rn((float)x, sp.ppx), sp.fx);
+            float p0, p1, p2;
+            int xi, yi;
+            deproject_tap<MODE>(sp, z16, x, y, nx, ny, p0, p1, p2, xi, yi);
+            const uint32_t rgb = load_rgb(job.color, xi * sp.bpp + yi * sp.stride);
+            rec[k] = make_record(sp.tf, p0, p1, p2, rgb);
+            if (FLOATOUT && job.xyzrgb) {
+                float4 f;
+                f.x = affine_row(sp.tf, 0, p0, p1, p2);
+                f.y = affine_row(sp.tf, 1, p0, p1, p2);
+                f.z = affine_row(sp.tf, 2, p0, p1, p2);
+                // pcl::PointXYZRGB colour word: b, g, r, a = 255
+                f.w = __uint_as_float(0xFF000000u | ((rgb & 0xFF) << 16) | (rgb & 0xFF00) | ((rgb >> 16) & 0xFF));
+                reinterpret_cast<float4 *>(job.xyzrgb)[p0i + k] = f;
+            }
+            if (CUTOFF) job.keep[p0i + k] = cutoff_keep(sp, p0, p2) ? 1 : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pack_pair(rec[2 * k], rec[2 * k + 1], w + 5 * k);
+    }
+    const int warp_oct0 = tile0 + warp * 32;
+    const int valid = min(32, octets - warp_oct0);
+    if (valid <= 0) return;
+    uint8_t *dst = reinterpret_cast<uint8_t *>(CUTOFF ? job.dense : job.payload) + (size_t)warp_oct0 * 80;
+    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    warp_store_records(slabs[warp], w, lane, dst, valid, aligned);
+    if (!CUTOFF && job.count && blockIdx.x == 0 && threadIdx.x == 0) *job.count = sp.N;
+}
+
+// ---------------------------------------------------------------------------
+// K1a: same inputs as the reference function.  One point per thread; a warp's 32
+// records (320 B) are staged in shared memory and leave as 16-byte stores.
+template <bool CUTOFF>
+__global__ void __launch_bounds__(256)
+k1a_vertices(const float *__restrict__ xyz, const float *__restrict__ uv, int n,
+             const uint8_t *__restrict__ color, const StreamParams *__restrict__ streams, int stream,
+             int16_t *__restrict__ out, uint8_t *__restrict__ keep) {
+    __shared__ __align__(16) uint16_t slabs[8][32 * 5];
+    const StreamParams &sp = streams[stream];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp_i0 = i - lane;
+    if (warp_i0 >= n) return;
+    if (i < n) {
+        const float p0 = __ldg(xyz + 3 * (size_t)i), p1 = __ldg(xyz + 3 * (size_t)i + 1),
+                    p2 = __ldg(xyz + 3 * (size_t)i + 2);
+        const float u = __ldg(uv + 2 * (size_t)i), v = __ldg(uv + 2 * (size_t)i + 1);
+        const int xi = tex_to_pixel(u, sp.cwf, sp.CW - 1);
+        const int yi = tex_to_pixel(v, sp.chf, sp.CH - 1);
+        const uint32_t rgb = load_rgb(color, xi * sp.bpp + yi * sp.stride);
+        const Rec r = make_record(sp.tf, p0, p1, p2, rgb);
+        uint16_t *s = slabs[warp] + lane * 5;
+        s[0] = (uint16_t)r.a; s[1] = (uint16_t)(r.a >> 16);
+        s[2] = (uint16_t)r.b; s[3] = (uint16_t)(r.b >> 16);
+        s[4] = (uint16_t)r.c;
+        if (CUTOFF) keep[i] = cutoff_keep(sp, p0, p2) ? 1 : 0;
+    }
+    __syncwarp();
+    const int valid = min(32, n - warp_i0);
+    uint8_t *dst = reinterpret_cast<uint8_t *>(out) + (size_t)warp_i0 * 10;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && valid == 32) {
+        if (lane < 20) st_global_v4(dst + lane * 16, reinterpret_cast<const uint4 *>(slabs[warp])[lane]);
+    } else {
+        uint16_t *d16 = reinterpret_cast<uint16_t *>(dst);
+        for (int c = lane; c < valid * 5; c += 32) d16[c] = slabs[warp][c];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// -c compaction, order preserving (the reference at -t 1 emits kept points in
+// raster order).  Point i is gated by the test of point (i ^ 3) when
+// lane_rev != 0 -- the reference's mask is reversed within each group of four
+//  -- else by its own test.
+constexpr int CMP_THREADS = 256, CMP_PER_THREAD = 8, CMP_TILE = CMP_THREADS * CMP_PER_THREAD;
+
+__device__ __forceinline__ int gate(const uint8_t *keep, int i, int lane_rev) {
+    return keep[lane_rev ? (i ^ 3) : i];
+}
+
+__global__ void __launch_bounds__(CMP_THREADS)
+compact_count(const uint8_t *__restrict__ keep, int n, int lane_rev, int32_t *__restrict__ tile_counts) {
+    __shared__ int warp_sums[CMP_THREADS / 32];
+    const int base = blockIdx.x * CMP_TILE + threadIdx.x * CMP_PER_THREAD;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < CMP_PER_THREAD; ++k)
+        if (base + k < n) c += gate(keep, base + k, lane_rev);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < CMP_THREADS / 32; ++k) t += warp_sums[k];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+// single block: exclusive scan of the tile counts, total to *count_out (and the
+// [int32] payload-size header when header != nullptr)
+__global__ void __launch_bounds__(1024)
+compact_scan(int32_t *__restrict__ tile_counts, int n_tiles, int32_t *__restrict__ count_out,
+             int32_t *__restrict__ total_slot) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_tiles ? tile_counts[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if ((threadIdx.x & 31) >= d) inc += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int t = warp_tot[threadIdx.x], inc2 = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, inc2, d);
+                if (threadIdx.x >= d) inc2 += u;
+            }
+            warp_tot[threadIdx.x] = inc2 - t;  // exclusive
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        if (i < n_tiles) tile_counts[i] = carry + warp_tot[threadIdx.x >> 5] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_tot[31] + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (count_out) *count_out = carry_s;
+        if (total_slot) *total_slot = carry_s;
+    }
+}
+
+__global__ void __launch_bounds__(CMP_THREADS)
+compact_scatter(const uint8_t *__restrict__ keep, const int16_t *__restrict__ dense, int n,
+                int lane_rev, const int32_t *__restrict__ tile_offsets, int16_t *__restrict__ out) {
+    __shared__ int warp_sums[CMP_THREADS / 32];
+    const int base = blockIdx.x * CMP_TILE + threadIdx.x * CMP_PER_THREAD;
+    int flags = 0, c = 0;
+#pragma unroll
+    for (int k = 0; k < CMP_PER_THREAD; ++k)
+        if (base + k < n && gate(keep, base + k, lane_rev)) { flags |= 1 << k; ++c; }
+    int inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((threadIdx.x & 31) >= d) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    int pos = tile_offsets[blockIdx.x] + inc - c;
+    for (int k = 0; k < (int)(threadIdx.x >> 5); ++k) pos += warp_sums[k];
+#pragma unroll
+    for (int k = 0; k < CMP_PER_THREAD; ++k) {
+        if (flags & (1 << k)) {
+            const int16_t *s = dense + 5 * (size_t)(base + k);
+            int16_t *d = out + 5 * (size_t)pos;
+            d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3]; d[4] = s[4];
+            ++pos;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Stitch side.  One table per launch, passed by value (fits the 4 KB parameter bank).
+struct CamTable {
+    const int16_t *src[MAX_CAMS];
+    int32_t n_in[MAX_CAMS];        // records available per camera
+    int32_t out_off[MAX_CAMS + 1]; // exclusive prefix of output records
+    int32_t n_cams, downsample;
+};
+struct TfTable {
+    float m[MAX_CAMS][12];
+};
+
+__device__ __forceinline__ int find_cam(const CamTable &t, int j) {
+    int c = 0;
+    while (c + 1 < t.n_cams && j >= t.out_off[c + 1]) ++c;
+    return c;
+}
+
+// 32 output records per warp, staged in shared memory, 16-byte stores.
+// stitched = [int32 bytes][records]; records start at stitched + 4.
+template <bool PCL>
+__global__ void __launch_bounds__(256)
+stitch_kernel(const __grid_constant__ CamTable tab, const __grid_constant__ TfTable tfs,
+              uint8_t *__restrict__ stitched, float4 *__restrict__ cloud32) {
+    __shared__ __align__(16) uint16_t slabs[8][32 * 5];
+    const int total = tab.out_off[tab.n_cams];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp_j0 = j - lane;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<int32_t *>(stitched) = total * 10;
+    if (warp_j0 >= total) return;
+    if (j < total) {
+        const int c = find_cam(tab, j);
+        const int16_t *s = tab.src[c] + 5 * (size_t)(j - tab.out_off[c]) * tab.downsample;
+        uint16_t r[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) r[k] = (uint16_t)__ldg(s + k);
+        if (PCL) {
+            // src/pcs-multicamera-optimized.cpp:237-242 then SPEC.md s2 then :255-259
+            const float x = __fdiv_rn((float)(int16_t)r[0], 1000.0f);
+            const float y = __fdiv_rn((float)(int16_t)r[1], 1000.0f);
+            const float z = __fdiv_rn((float)(int16_t)r[2], 1000.0f);
+            const float *m = tfs.m[c];
+            const float ox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), m[3]);
+            const float oy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], x), __fmul_rn(m[5], y)), __fmul_rn(m[6], z)), m[7]);
+            const float oz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], x), __fmul_rn(m[9], y)), __fmul_rn(m[10], z)), m[11]);
+            r[0] = (uint16_t)to_mm16(ox);
+            r[1] = (uint16_t)to_mm16(oy);
+            r[2] = (uint16_t)to_mm16(oz);
+            r[4] &= 0xFF;  // b = buffer[4] & 0xFF (:242)
+            if (cloud32) {
+                const uint32_t bgra = 0xFF000000u | ((uint32_t)(r[3] & 0xFF) << 16) | (r[3] & 0xFF00u) | r[4];
+                cloud32[2 * (size_t)j] = make_float4(ox, oy, oz, 1.0f);
+                cloud32[2 * (size_t)j + 1] = make_float4(__uint_as_float(bgra), 0.f, 0.f, 0.f);
+            }
+        }
+        uint16_t *d = slabs[warp] + lane * 5;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) d[k] = r[k];
+    }
+    __syncwarp();
+    const int valid = min(32, total - warp_j0);
+    uint8_t *dst = stitched + 4 + (size_t)warp_j0 * 10;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && valid == 32) {
+        if (lane < 20) st_global_v4(dst + lane * 16, reinterpret_cast<const uint4 *>(slabs[warp])[lane]);
+    } else {
+        uint16_t *d16 = reinterpret_cast<uint16_t *>(dst);
+        for (int k = lane; k < valid * 5; k += 32) d16[k] = slabs[warp][k];
+    }
+}
+
+}  // namespace pcs

@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# the product library and the oracle are build artefacts (git-ignored): make sure they exist
+import __graft_entry__  # noqa: E402
+
+__graft_entry__.build()
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")

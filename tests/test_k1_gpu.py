@@ -1,0 +1,270 @@
+"""-m gpu parity tests, camera side: the CUDA path through the C ABI against
+(a) the golden fixtures produced by the reference's own compiled functions and
+(b) the oracle restatement on full-size seeded frames.  Bit-exact on all 10
+bytes of every record; float XYZ within 1e-5 relative (north_star)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import oracle  # noqa: E402
+import pointcloud_stitching_b200 as pcs  # noqa: E402
+from gpu_util import calib_and_desc, dev, run_batch, small_rotation  # noqa: E402
+from pointcloud_stitching_b200 import synth  # noqa: E402
+
+VARIANTS = [1]  # 1 = direct, 2 = bulk-async pipelined (added once the kernel lands)
+
+
+@pytest.fixture(scope="module")
+def R():
+    return oracle.restatement()
+
+
+@pytest.fixture(scope="module", params=VARIANTS)
+def ctx(request):
+    c = pcs.Context(device=0, max_streams=8, kernel_variant=request.param)
+    c.variant = request.param
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx0():
+    c = pcs.Context(device=0, max_streams=8)
+    yield c
+    c.close()
+
+
+# ------------------------------------------------------------------ golden fixtures
+@pytest.mark.parametrize("name", ["pack_96x64_identity", "pack_96x64_baseline", "pack_96x64_cutoff"])
+def test_fused_kernel_vs_reference_golden(ctx0, name):
+    g = load_golden(name)
+    w, h = int(g["w"]), int(g["h"])
+    cut = bool(g["cutoff"])
+    ctx0.set_stream(0, pcs.stream_desc(w, h, tf=g["tf"], translation=tuple(g["translation"]), cutoff=cut))
+    size, buf = ctx0.send_xyzrgb(0, g["z16"], g["color"])
+    want = g["out_records"]
+    assert size == want.shape[0] * 10
+    assert np.array_equal(buf[2:2 + want.size].reshape(-1, 5), want)
+
+
+@pytest.mark.parametrize("name", ["pack_96x64_identity", "pack_96x64_baseline", "pack_96x64_cutoff",
+                                  "pack_adversarial", "pack_adversarial_cutoff"])
+def test_from_vertices_vs_reference_golden(ctx0, name):
+    g = load_golden(name)
+    w, h = int(g["w"]), int(g["h"])
+    stride = int(g["stride"]) if "stride" in g else w * 3
+    ctx0.set_stream(1, pcs.stream_desc(w, h, tf=g["tf"], stride=stride, cutoff=bool(g["cutoff"])))
+    got = ctx0.pack_from_vertices(1, g["xyz"], g["uv"], g["color"])
+    assert np.array_equal(got, g["out_records"])
+
+
+def test_camera_buffer_image_vs_reference_golden(ctx0):
+    g = load_golden("send_64x32")
+    w, h = int(g["w"]), int(g["h"])
+    n5 = w * h * 5 + 64
+    ctx0.set_stream(0, pcs.stream_desc(w, h, tf=g["tf"]))
+    size, buf = ctx0.send_xyzrgb(0, g["z16"], g["color"], write_header=False)
+    assert size == int(g["size"])
+    assert np.array_equal(buf[:n5], g["out_head_nosend"])
+    assert np.array_equal(buf[2499990:2500010], g["out_memset_edge"])
+    assert np.all(buf[2500000:] == 0x5A5A)                      # memset stops at byte 5 000 000
+    size, buf = ctx0.send_xyzrgb(0, g["z16"], g["color"], write_header=True)
+    assert np.array_equal(buf[:n5], g["out_head_send"])
+    assert np.array_equal(buf.view(np.uint8)[: size + 4], g["wire_bytes"])
+
+
+# ------------------------------------------------------------------ full frames vs oracle
+CASES = {
+    "720p_aligned": dict(w=1280, h=720),
+    "720p_baseline": dict(w=1280, h=720, translation=synth.D2C_BASELINE),
+    "720p_rotated": dict(w=1280, h=720, translation=(0.015, -0.002, 0.001), rotation=small_rotation()),
+    "480p_aligned": dict(w=848, h=480),
+    "480p_baseline": dict(w=848, h=480, translation=synth.D2C_BASELINE),
+    "720p_color1080p": dict(w=1280, h=720, cw=1920, ch=1080, translation=synth.D2C_BASELINE),
+    "720p_rgba_padded": dict(w=1280, h=720, bpp=4, stride=1280 * 4 + 64, translation=synth.D2C_BASELINE),
+    "odd_intrinsics": dict(w=640, h=360, translation=(0.02, 0.01, -0.005), dfx=381.7, dfy=380.9,
+                           dppx=322.3, dppy=178.8, cfx=610.2, cfy=611.9, cppx=318.4, cppy=182.1),
+    "tiny_8x1": dict(w=8, h=1),
+    "narrow_24x5": dict(w=24, h=5, translation=synth.D2C_BASELINE),
+}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_fused_kernel_vs_oracle(ctx, R, case):
+    kw = dict(CASES[case])
+    w, h = kw.pop("w"), kw.pop("h")
+    cw, ch = kw.pop("cw", w), kw.pop("ch", h)
+    bpp, stride = kw.pop("bpp", 3), kw.pop("stride", None)
+    stride = cw * bpp if stride is None else stride
+    cal, desc = calib_and_desc(w, h, cw, ch, tf=synth.TF_STITCH[1], bpp=bpp, stride=stride, **kw)
+    ctx.set_stream(0, desc)
+    jobs = []
+    for f in range(2):
+        z = synth.depth_frame(w, h, 3, f)
+        col = synth.color_frame(cw, ch, 3, f, stride=stride, bpp=bpp)
+        jobs.append((0, z, col))
+    got = run_batch(ctx, jobs, None)
+    for (_, z, col), (rec, _, _) in zip(jobs, got):
+        want = R.frame(cal, z, col, bpp, stride, synth.TF_STITCH[1])
+        assert rec.shape == want.shape
+        bad = np.nonzero((rec != want).any(axis=1))[0]
+        assert bad.size == 0, "first mismatches at points %s: got %s want %s" % (bad[:5], rec[bad[:5]], want[bad[:5]])
+
+
+def test_extreme_depths(ctx, R):
+    # z16 = 1 and 65535 everywhere, checkerboard with holes
+    w, h = 256, 64
+    for trans in [(0.0, 0.0, 0.0), synth.D2C_BASELINE]:
+        cal, desc = calib_and_desc(w, h, tf=synth.TF_STITCH[7], translation=trans)
+        ctx.set_stream(2, desc)
+        z = np.zeros((h, w), np.uint16)
+        z[::2, ::2] = 65535
+        z[1::2, 1::2] = 1
+        z[::3, 1::4] = 32768
+        col = synth.color_frame(w, h, 9, 9)
+        (rec, _, _), = run_batch(ctx, [(2, z, col)], None)
+        assert np.array_equal(rec, R.frame(cal, z, col, 3, w * 3, synth.TF_STITCH[7]))
+
+
+def test_heterogeneous_batch(ctx, R):
+    # several streams of different geometry and tex mode in one batch
+    specs = [dict(w=1280, h=720), dict(w=848, h=480, translation=synth.D2C_BASELINE),
+             dict(w=640, h=480, translation=(0.01, 0, 0), rotation=small_rotation(0.02, 0.01, -0.01))]
+    cals, jobs = [], []
+    for s, kw in enumerate(specs):
+        kw = dict(kw)
+        w, h = kw.pop("w"), kw.pop("h")
+        cal, desc = calib_and_desc(w, h, tf=synth.TF_STITCH[s], **kw)
+        ctx.set_stream(s, desc)
+        cals.append((cal, w, h))
+        for f in range(3):
+            jobs.append((s, synth.depth_frame(w, h, s, f), synth.color_frame(w, h, s, f)))
+    got = run_batch(ctx, jobs, None)
+    for (s, z, col), (rec, _, _) in zip(jobs, got):
+        cal, w, h = cals[s]
+        assert np.array_equal(rec, R.frame(cal, z, col, 3, w * 3, synth.TF_STITCH[s]))
+
+
+def test_float_xyzrgb_output(ctx0, R):
+    w, h = 640, 360
+    cal, desc = calib_and_desc(w, h, tf=synth.TF_STITCH[4], translation=synth.D2C_BASELINE)
+    ctx0.set_stream(0, desc)
+    z, col = synth.depth_frame(w, h, 1, 2), synth.color_frame(w, h, 1, 2)
+    (rec, fo, _), = run_batch(ctx0, [(0, z, col)], None, float_out=True)
+    xyz, uv = R.deproject(cal, z)
+    want_rec = R.pack(xyz, uv, col, w, h, 3, w * 3, synth.TF_STITCH[4])
+    assert np.array_equal(rec, want_rec)
+    want_xyz = R.transform_points(xyz, synth.TF_STITCH[4])
+    # north_star tolerance: 1e-5 relative on float XYZ (the kernel's FMA chain is in fact exact)
+    assert np.allclose(fo[:, :3], want_xyz, rtol=1e-5, atol=0)
+    bgra = fo[:, 3].copy().view(np.uint32)
+    r, g_, b = want_rec[:, 3].view(np.uint16) & 0xFF, want_rec[:, 3].view(np.uint16) >> 8, want_rec[:, 4] & 0xFF
+    assert np.array_equal(bgra, (0xFF << 24) | (r.astype(np.uint32) << 16) | (g_.astype(np.uint32) << 8) | b.astype(np.uint32))
+
+
+@pytest.mark.parametrize("lane_reversed", [True, False])
+def test_cutoff_compaction(ctx0, R, lane_reversed):
+    w, h = 1280, 720
+    cal, desc = calib_and_desc(w, h, tf=synth.TF_CAMERA, translation=synth.D2C_BASELINE, cutoff=True)
+    desc.cutoff_lane_reversed = int(lane_reversed)
+    ctx0.set_stream(3, desc)
+    z = synth.depth_frame(w, h, 4, 4, lo=300, hi=2600)
+    col = synth.color_frame(w, h, 4, 4)
+    xyz, uv = R.deproject(cal, z)
+    if lane_reversed:
+        want = R.pack(xyz, uv, col, w, h, 3, w * 3, synth.TF_CAMERA, cutoff=True)   # reference order + quirk
+    else:
+        dense = R.pack(xyz, uv, col, w, h, 3, w * 3, synth.TF_CAMERA)
+        keep = (xyz[:, 2] > 0) & (xyz[:, 2] <= 1.5) & (xyz[:, 0] > -2) & (xyz[:, 0] <= 2)
+        want = dense[keep]
+    assert 1000 < len(want) < w * h
+    (rec, _, cnt), = run_batch(ctx0, [(3, z, col)], None, want_count=True)
+    assert cnt == len(want) and np.array_equal(rec, want)
+    size, buf = ctx0.send_xyzrgb(3, z, col, write_header=True)
+    assert size == len(want) * 10 and buf.view(np.int32)[0] == size
+    assert np.array_equal(buf[2:2 + want.size].reshape(-1, 5), want)
+    assert np.all(buf[2 + want.size:2500000] == 0)              # memset region past the records
+    got = ctx0.pack_from_vertices(3, xyz, uv, col)
+    assert np.array_equal(got, want)
+
+
+def test_from_vertices_full_frame_vs_oracle(ctx0, R):
+    w, h = 1280, 720
+    cal, desc = calib_and_desc(w, h, tf=synth.TF_STITCH[2], translation=synth.D2C_BASELINE)
+    ctx0.set_stream(0, desc)
+    z, col = synth.depth_frame(w, h, 5, 1), synth.color_frame(w, h, 5, 1)
+    xyz, uv = R.deproject(cal, z)
+    got = ctx0.pack_from_vertices(0, xyz, uv, col)
+    assert np.array_equal(got, R.pack(xyz, uv, col, w, h, 3, w * 3, synth.TF_STITCH[2]))
+    # n % 8 == 4 tail, and n = 0
+    assert np.array_equal(ctx0.pack_from_vertices(0, xyz[:1004], uv[:1004], col),
+                          R.pack(xyz[:1004], uv[:1004], col, w, h, 3, w * 3, synth.TF_STITCH[2]))
+    assert len(ctx0.pack_from_vertices(0, xyz[:0], uv[:0], col)) == 0
+    with pytest.raises(pcs.PcsError):
+        ctx0.pack_from_vertices(0, xyz[:6], uv[:6], col)        # reference needs n % 4 == 0
+
+
+def test_linearity_of_transform_property(ctx0):
+    # size-independent property at full size: records of frame under tf2 o identity-depth shift...
+    # translating the world transform by whole millimetres shifts every int16 coordinate by that much
+    w, h = 1280, 720
+    z, col = synth.depth_frame(w, h, 6, 0), synth.color_frame(w, h, 6, 0)
+    tf_a = synth.IDENTITY.copy()
+    tf_b = synth.IDENTITY.copy()
+    tf_b[3], tf_b[7], tf_b[11] = 1.0, -2.0, 3.0                 # exact in fp32, result exact multiples
+    ctx0.set_stream(0, pcs.stream_desc(w, h, tf=tf_a))
+    ctx0.set_stream(1, pcs.stream_desc(w, h, tf=tf_b))
+    (a, _, _), (b, _, _) = run_batch(ctx0, [(0, z, col), (1, z, col)], None)
+    assert np.array_equal(a[:, 3:], b[:, 3:])
+    d = b[:, :3].astype(np.int32) - a[:, :3].astype(np.int32)
+    # |coords| < 8 m here, so x + 1.0 etc. round at 2^-21: truncation may differ by one LSB at most
+    assert np.all(np.abs(d - np.array([1000, -2000, 3000])) <= 1)
+    assert (d == np.array([1000, -2000, 3000])).mean() > 0.99
+
+
+def test_async_begin_end_many_streams(ctx0, R):
+    w, h = 848, 480
+    bufs, want = [], []
+    for s in range(4):
+        cal, desc = calib_and_desc(w, h, tf=synth.TF_STITCH[s], translation=synth.D2C_BASELINE)
+        ctx0.set_stream(s, desc)
+        z = ctx0.host_alloc(w * h * 2, np.uint16)
+        z[:] = synth.depth_frame(w, h, s, 7).reshape(-1)
+        col = ctx0.host_alloc(w * h * 3, np.uint8)
+        col[:] = synth.color_frame(w, h, s, 7).reshape(-1)
+        buf = ctx0.new_camera_buffer(pinned=True)
+        bufs.append((z, col, buf))
+        want.append(R.frame(cal, z.reshape(h, w), col.reshape(h, w * 3), 3, w * 3, synth.TF_STITCH[s]))
+    for s, (z, col, buf) in enumerate(bufs):
+        ctx0.send_begin(s, z, col, buf, write_header=True)
+    with pytest.raises(pcs.PcsError):
+        ctx0.send_begin(0, *bufs[0])                            # one frame in flight per stream
+    for s, (z, col, buf) in enumerate(bufs):
+        assert ctx0.send_end(s) == w * h * 10
+        assert np.array_equal(buf[2:2 + w * h * 5].reshape(-1, 5), want[s])
+        assert buf.view(np.int32)[0] == w * h * 10
+
+
+def test_error_paths(ctx0):
+    with pytest.raises(pcs.PcsError) as e:
+        ctx0.send_xyzrgb(7, np.zeros(8, np.uint16), np.zeros(24, np.uint8))
+    assert e.value.status == pcs.PCS_ERR_INVALID and "not configured" in str(e.value)
+    with pytest.raises(pcs.PcsError):
+        ctx0.set_stream(99, pcs.stream_desc(8, 1))
+    with pytest.raises(pcs.PcsError):
+        ctx0.set_stream(0, pcs.stream_desc(8, 1, bpp=2))
+    ctx0.set_stream(5, pcs.stream_desc(1284, 4))                  # width % 8 != 0
+    with pytest.raises(pcs.PcsError) as e:
+        ctx0.send_xyzrgb(5, np.zeros(1284 * 4, np.uint16), np.zeros(1284 * 4 * 3, np.uint8))
+    assert e.value.status == pcs.PCS_ERR_UNSUPPORTED
+    ctx0.set_stream(5, pcs.stream_desc(1280, 720))
+    t = torch.zeros(1280 * 720 + 8, dtype=torch.int16, device="cuda")
+    with pytest.raises(pcs.PcsError):                            # misaligned depth pointer
+        ctx0.batch([(5, t.data_ptr() + 2, t.data_ptr(), t.data_ptr())])

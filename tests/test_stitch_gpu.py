@@ -1,0 +1,132 @@
+"""-m gpu parity tests, stitch side (concat / decimate, unpack-transform-append-repack,
+voxel merge) through the C ABI against the reference's golden vectors and the oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, roundtrip_inputs
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import oracle  # noqa: E402
+import pointcloud_stitching_b200 as pcs  # noqa: E402
+from gpu_util import dev  # noqa: E402
+from pointcloud_stitching_b200 import synth  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def R():
+    return oracle.restatement()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pcs.Context(device=0, max_streams=2)
+    yield c
+    c.close()
+
+
+def random_records(rng, n):
+    rec = rng.integers(-32768, 32768, (n, 5), dtype=np.int16)
+    rec[:, 4] = rng.integers(0, 256, n)          # the wire format keeps the 10th byte zero
+    return rec
+
+
+def test_stitch_vs_reference_golden(ctx):
+    g = load_golden("stitch_2048")
+    rec = g["records"]
+    for d in (1, 2, 3, 4, 7):
+        assert np.array_equal(ctx.stitch_raw([rec], d), g["out_raw_d%d" % d])
+    for d in (1, 2, 4):
+        for k in (0, 5):
+            assert np.array_equal(ctx.stitch_pcl([rec], [synth.TF_STITCH[k]], d), g["out_pcl_d%d_tf%d" % (d, k)])
+
+
+def test_lossy_roundtrip_vs_reference_golden(ctx):
+    # identity transform still changes 740 of the 65 536 int16 values
+    allv = roundtrip_inputs()
+    diff = load_golden("roundtrip_all_int16")["out_minus_in"].astype(np.int32)
+    out = ctx.stitch_pcl([allv], [synth.IDENTITY], 1)
+    rec = out[4:].view(np.int16).reshape(-1, 5)
+    assert np.array_equal(rec.astype(np.int32) - allv.astype(np.int32), diff)
+
+
+@pytest.mark.parametrize("n_cams,downsample", [(1, 1), (4, 1), (4, 2), (8, 3), (20, 1), (20, 5)])
+def test_multi_camera_vs_oracle(ctx, R, n_cams, downsample):
+    rng = np.random.default_rng(n_cams * 10 + downsample)
+    sizes = [int(rng.integers(0, 30000)) for _ in range(n_cams)]
+    sizes[0] = 40960
+    if n_cams > 2:
+        sizes[2] = 0                              # a camera that sent nothing
+    pay = [random_records(rng, n) for n in sizes]
+    tfs = [synth.TF_STITCH[k % 8] for k in range(n_cams)]
+    assert np.array_equal(ctx.stitch_raw(pay, downsample), R.concat(pay, downsample))
+    assert np.array_equal(ctx.stitch_pcl(pay, tfs, downsample), R.pcl_stitch(pay, tfs, downsample))
+
+
+def test_device_path_and_cloud32(ctx, R):
+    rng = np.random.default_rng(5)
+    pay = [random_records(rng, n) for n in (921600, 407040, 8, 123457)]
+    tfs = [synth.TF_STITCH[k] for k in range(4)]
+    d = [dev(p.reshape(-1)) for p in pay]
+    total = sum(p.shape[0] for p in pay)
+    st = torch.zeros(total * 10 + 16 + 16, dtype=torch.uint8, device="cuda")
+    cloud = torch.zeros(total * 8, dtype=torch.float32, device="cuda")
+    base = st.data_ptr() + 12                     # header at +12 so the records are 16-byte aligned
+    cs = torch.cuda.current_stream().cuda_stream
+    size = ctx.stitch_raw_dev([t.data_ptr() for t in d], [p.size for p in pay], 1, base, total * 10 + 4, cs)
+    torch.cuda.synchronize()
+    assert np.array_equal(st[12:12 + size + 4].cpu().numpy(), R.concat(pay, 1))
+    size = ctx.stitch_pcl_dev([t.data_ptr() for t in d], [p.size for p in pay], 1, tfs, base, total * 10 + 4,
+                              cloud.data_ptr(), cs)
+    torch.cuda.synchronize()
+    assert np.array_equal(st[12:12 + size + 4].cpu().numpy(), R.pcl_stitch(pay, tfs, 1))
+    want = np.concatenate([R.transform_cloud(R.unpack(p), t) for p, t in zip(pay, tfs)])
+    got = cloud.cpu().numpy().view(oracle.PCLPOINT)
+    for f in ("x", "y", "z", "w", "b", "g", "r", "a"):
+        assert np.array_equal(got[f], want[f]), f
+    # unaligned stitched buffer (header at +0): same bytes through the 2-byte store path
+    size = ctx.stitch_raw_dev([t.data_ptr() for t in d], [p.size for p in pay], 2, st.data_ptr(), total * 10 + 4, cs)
+    torch.cuda.synchronize()
+    assert np.array_equal(st[: size + 4].cpu().numpy(), R.concat(pay, 2))
+
+
+def test_stitch_errors(ctx):
+    rec = np.zeros((16, 5), np.int16)
+    with pytest.raises(pcs.PcsError):
+        ctx.stitch_raw([rec], 0)
+    with pytest.raises(pcs.PcsError):
+        ctx.stitch_raw([rec] * 33, 1)
+    with pytest.raises(pcs.PcsError) as e:
+        ctx.stitch_raw_dev([0], [80], 1, 0, 4)
+    assert e.value.status == pcs.PCS_ERR_INVALID
+    t = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    with pytest.raises(pcs.PcsError) as e:       # capacity check
+        ctx.stitch_raw_dev([t.data_ptr()], [80], 1, t.data_ptr(), 100)
+    assert e.value.status == pcs.PCS_ERR_CAPACITY
+
+
+def test_voxel_merge_vs_oracle(ctx, R):
+    rng = np.random.default_rng(11)
+    for n, span, leaf in [(50000, 2000, 10), (200000, 400, 10), (5000, 30000, 25), (4, 10, 10), (1, 5, 1)]:
+        rec = random_records(rng, n)
+        rec[:, :3] = rng.integers(-span, span, (n, 3))
+        assert np.array_equal(ctx.voxel_merge(rec, leaf), R.voxel_merge(rec, leaf)), (n, span, leaf)
+    assert len(ctx.voxel_merge(np.zeros((0, 5), np.int16), 10)) == 0
+
+
+def test_voxel_merge_full_size_properties(ctx):
+    # 4 cameras x 1280x720 of plausible geometry: idempotence, sortedness, bounds
+    rng = np.random.default_rng(12)
+    n = 4 * 921600
+    rec = random_records(rng, n)
+    rec[:, :3] = (rng.normal(0, 1500, (n, 3))).clip(-32000, 32000).astype(np.int16)
+    m = ctx.voxel_merge(rec, 10)
+    k = np.floor_divide(m[:, :3].astype(np.int64), 10)
+    key = (k[:, 2] << 40) + (k[:, 1] << 20) + k[:, 0]
+    assert np.all(np.diff(key) > 0)
+    assert np.array_equal(ctx.voxel_merge(m, 10), m)
+    assert len(m) == len(np.unique(np.floor_divide(rec[:, :3].astype(np.int32), 10), axis=0))
