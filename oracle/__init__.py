@@ -195,10 +195,10 @@ class Restatement:
         clouds = [self.transform_cloud(self.unpack(p, downsample), t)
                   for p, t in zip(payloads, transforms)]
         rec = self.repack(np.concatenate(clouds)) if clouds else np.zeros((0, 5), np.int16)
-        out = np.zeros(rec.size + 2, np.int16)
-        out[2:] = rec.reshape(-1)
-        out.view(np.int32)[0] = rec.size * 2
-        return out.view(np.uint8)
+        out = np.zeros(rec.size * 2 + 4, np.uint8)
+        out[:4] = np.frombuffer(np.int32(rec.size * 2).tobytes(), np.uint8)
+        out[4:] = rec.reshape(-1).view(np.uint8)
+        return out
 
     def voxel_merge(self, records, leaf_mm=10):
         rec = np.ascontiguousarray(records, dtype=np.int16).reshape(-1, 5)
