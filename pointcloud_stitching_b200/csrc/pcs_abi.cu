@@ -138,6 +138,10 @@ int pick_tex_mode(const pcs_stream_desc &d) {
                       d.depth.ppy >= 0.f && d.depth.ppy <= (float)d.depth.height &&
                       d.depth_scale >= 1e-6f && d.depth_scale <= 1.0f;
     if (t0 && same && sane) return TEX_ALIGNED;
+    // translation along x only, same image size and vertical intrinsics: tap row == pixel row
+    const bool same_v = d.depth.width == d.color.width && d.depth.height == d.color.height &&
+                        d.depth.fy == d.color.fy && d.depth.ppy == d.color.ppy;
+    if (same_v && sane && d.d2c_translation[1] == 0.f && d.d2c_translation[2] == 0.f) return TEX_TRANSLATE_X;
     return TEX_TRANSLATE;
 }
 
@@ -228,6 +232,7 @@ void launch_k1_direct(int tex_mode, bool cutoff, bool floatout, dim3 grid, cudaS
     switch (tex_mode) {
         case TEX_ALIGNED: launch_k1_mode<TEX_ALIGNED>(cutoff, floatout, grid, cs, jobs, params); break;
         case TEX_TRANSLATE: launch_k1_mode<TEX_TRANSLATE>(cutoff, floatout, grid, cs, jobs, params); break;
+        case TEX_TRANSLATE_X: launch_k1_mode<TEX_TRANSLATE_X>(cutoff, floatout, grid, cs, jobs, params); break;
         default: launch_k1_mode<TEX_GENERAL>(cutoff, floatout, grid, cs, jobs, params); break;
     }
 }
@@ -538,8 +543,8 @@ int pcs_b200_batch_create(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs, p
     auto bail = [&](int rc) { pcs_b200_batch_destroy(ctx, b); return rc; };
     // order jobs by kernel variant so that each variant is one launch
     std::vector<int> order;
-    for (int v = 0; v < 12; ++v) {
-        const int tm = v % 3, cut = (v / 3) & 1, fo = v / 6;
+    for (int v = 0; v < 16; ++v) {
+        const int tm = v % 4, cut = (v / 4) & 1, fo = v / 8;
         pcs_batch::Group g{tm, cut, fo, (int)order.size(), 0, 0, 0};
         for (int j = 0; j < n_jobs; ++j) {
             int rc = check_stream(ctx, jobs[j].stream, true);

@@ -15,7 +15,8 @@ namespace pcs {
 enum TexMode : int {
     TEX_GENERAL = 0,    // full rotation + translation, then projection
     TEX_TRANSLATE = 1,  // rotation is exactly the identity: R*p + T == p + T bit for bit
-    TEX_ALIGNED = 2     // identity extrinsics and equal intrinsics: the tap is the pixel itself
+    TEX_ALIGNED = 2,    // identity extrinsics and equal intrinsics: the tap is the pixel itself
+    TEX_TRANSLATE_X = 3 // translation along x only, equal vertical intrinsics: the tap ROW is the pixel's own
 };
 
 // Per-stream constants (pcs_stream_desc, pre-digested on the host).
@@ -83,6 +84,20 @@ __device__ __forceinline__ void deproject_tap(const StreamParams &s, uint32_t z1
         // SPEC.md s1: the chain's rounding error is < 1e-3 px, so a valid pixel taps itself
         const bool valid = depth != 0.0f;
         xi = valid ? x : 0;
+        yi = valid ? y : 0;
+        return;
+    }
+    if (MODE == TEX_TRANSLATE_X) {
+        // t1 == p1 and t2 == p2 exactly, so the row follows the TEX_ALIGNED argument; only the
+        // column needs the projection chain
+        float u = 0.0f;
+        const bool valid = depth != 0.0f;
+        if (valid) {
+            const float t0 = __fadd_rn(p0, s.T[0]);
+            const float px = __fadd_rn(__fmul_rn(__fdiv_rn(t0, p2), s.cfx), s.cppx);
+            u = __fdiv_rn(px, s.cwf);
+        }
+        xi = tex_to_pixel(u, s.cwf, s.CW - 1);
         yi = valid ? y : 0;
         return;
     }

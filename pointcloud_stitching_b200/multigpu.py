@@ -1,0 +1,101 @@
+"""Multi-GPU stitch: one process per GPU, cameras sharded in contiguous blocks, and an
+in-place gather of the packed XYZRGB records into the reference's stitched-buffer layout.
+
+The reference fans N camera streams into one host over TCP and concatenates them in
+camera-index order behind an int32 byte count
+(src/pcs-multicamera-client.cpp:381-395).  Here every rank's K1 writes its cameras'
+records straight into their slots of a replicated stitched buffer, so the "concat" is
+free, and the exchange is one collective over NVLink:
+
+* equal shards  -> ``all_gather_into_tensor`` in place (send = recv + rank * count);
+* ragged shards -> one ``broadcast`` per rank of that rank's slot (all-gather-v), e.g.
+  20 cameras on 8 GPUs = 3,3,3,3,2,2,2,2.
+
+torch.distributed is plumbing only (NCCL on GPUs, gloo in the CPU tests); no kernels here.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+RECORD_BYTES = 10
+#: records start here so that they are 16-byte aligned; the int32 header sits at PAD - 4
+PAD = 16
+
+
+def partition(n_cams: int, world: int):
+    """Contiguous blocks in camera order: the first n_cams % world ranks take one more."""
+    base, extra = divmod(n_cams, world)
+    out, start = [], 0
+    for r in range(world):
+        k = base + (1 if r < extra else 0)
+        out.append(list(range(start, start + k)))
+        start += k
+    return out
+
+
+class StitchLayout:
+    """Byte offsets of every camera's slot in the stitched payload (camera-index order)."""
+
+    def __init__(self, points_per_cam, world):
+        self.points = [int(p) for p in points_per_cam]
+        self.world = world
+        self.cams_of = partition(len(self.points), world)
+        self.cam_offset = np.concatenate([[0], np.cumsum([p * RECORD_BYTES for p in self.points])]).astype(np.int64)
+        self.total_bytes = int(self.cam_offset[-1])
+        self.rank_offset, self.rank_bytes = [], []
+        for cams in self.cams_of:
+            lo = int(self.cam_offset[cams[0]]) if cams else self.total_bytes
+            hi = int(self.cam_offset[cams[-1] + 1]) if cams else self.total_bytes
+            self.rank_offset.append(lo)
+            self.rank_bytes.append(hi - lo)
+        self.equal = len(set(self.rank_bytes)) == 1 and self.rank_bytes[0] > 0
+        if self.total_bytes > 0x7FFFFFFF:
+            raise ValueError("stitched payload exceeds the reference's int32 size header")
+
+    def rank_of(self, cam):
+        for r, cams in enumerate(self.cams_of):
+            if cam in cams:
+                return r
+        raise IndexError(cam)
+
+
+class StitchedBuffer:
+    """A replicated stitched buffer ``[int32 bytes][cam0 records][cam1 records]...`` and its exchange."""
+
+    def __init__(self, layout: StitchLayout, rank: int, device):
+        self.layout, self.rank = layout, rank
+        self.raw = torch.zeros(PAD + layout.total_bytes, dtype=torch.uint8, device=device)
+        self.payload = self.raw[PAD:]
+        hdr = np.frombuffer(np.int32(layout.total_bytes).tobytes(), np.uint8).copy()
+        self.raw[PAD - 4:PAD] = torch.from_numpy(hdr).to(device)
+
+    def slot(self, cam):
+        """uint8 view of one camera's records."""
+        o = self.layout.cam_offset
+        return self.payload[int(o[cam]):int(o[cam + 1])]
+
+    def slot_ptr(self, cam):
+        return self.payload.data_ptr() + int(self.layout.cam_offset[cam])
+
+    def my_cams(self):
+        return self.layout.cams_of[self.rank]
+
+    def gather(self, group=None):
+        """In place: afterwards every rank holds every camera's records."""
+        L = self.layout
+        if L.world == 1:
+            return
+        if L.equal:
+            n = L.rank_bytes[0]
+            mine = self.payload[self.rank * n:(self.rank + 1) * n]
+            dist.all_gather_into_tensor(self.payload, mine, group=group)
+        else:
+            for r in range(L.world):
+                if L.rank_bytes[r]:
+                    dist.broadcast(self.payload[L.rank_offset[r]:L.rank_offset[r] + L.rank_bytes[r]], src=r, group=group)
+
+    def wire_bytes(self):
+        """``[int32 bytes][records]`` exactly as the reference writes it to the viewer socket."""
+        return self.raw[PAD - 4:]

@@ -145,6 +145,29 @@ def test_extreme_depths(ctx, R):
         assert np.array_equal(rec, R.frame(cal, z, col, 3, w * 3, synth.TF_STITCH[7]))
 
 
+@pytest.mark.parametrize("w,h", [(1280, 720), (848, 480)])
+def test_every_depth_value_at_every_column(ctx, R, w, h):
+    """Exhaustive over the kernel's data-dependent arithmetic: every z16 in 0..65535 at every
+    column (rows of constant depth), 15 mm baseline, so that every (t0 / depth, px / width)
+    division the tap chain can meet at this geometry is compared with the oracle."""
+    cal, desc = calib_and_desc(w, h, tf=synth.TF_STITCH[5], translation=synth.D2C_BASELINE)
+    ctx.set_stream(0, desc)
+    n_frames = -(-65536 // h)
+    col = synth.color_frame(w, h, 11, 0)
+    jobs = []
+    for f in range(n_frames):
+        z = ((np.arange(h, dtype=np.int64) + f * h) % 65536).astype(np.uint16)
+        jobs.append((0, np.repeat(z[:, None], w, axis=1), col))
+    for lo in range(0, n_frames, 32):
+        chunk = jobs[lo:lo + 32]
+        got = run_batch(ctx, chunk, None)
+        for (_, z, c), (rec, _, _) in zip(chunk, got):
+            want = R.frame(cal, z, c, 3, w * 3, synth.TF_STITCH[5])
+            bad = np.nonzero((rec != want).any(axis=1))[0]
+            assert bad.size == 0, "z16=%d x=%d: got %s want %s" % (
+                z.reshape(-1)[bad[0]], bad[0] % w, rec[bad[0]], want[bad[0]])
+
+
 def test_heterogeneous_batch(ctx, R):
     # several streams of different geometry and tex mode in one batch
     specs = [dict(w=1280, h=720), dict(w=848, h=480, translation=synth.D2C_BASELINE),

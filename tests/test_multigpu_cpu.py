@@ -1,0 +1,71 @@
+"""N > 1 host logic on CPU: world_size-2 gloo processes shard the cameras, fill their slots of
+the replicated stitched buffer (records come from the oracle here -- there is no GPU), run the
+in-place exchange and must end up with the reference's stitched layout
+(src/pcs-multicamera-client.cpp:385-395) byte for byte."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pointcloud_stitching_b200 import multigpu, synth
+
+
+def test_partition_and_layout():
+    assert multigpu.partition(20, 8) == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 10, 11], [12, 13], [14, 15],
+                                         [16, 17], [18, 19]]
+    assert multigpu.partition(8, 8) == [[k] for k in range(8)]
+    assert multigpu.partition(3, 4) == [[0], [1], [2], []]
+    L = multigpu.StitchLayout([407040] * 20, 8)
+    assert L.total_bytes == 81408000 and not L.equal
+    assert L.rank_offset[4] == 12 * 4070400 and L.rank_bytes[4] == 2 * 4070400
+    assert L.rank_of(13) == 4
+    assert multigpu.StitchLayout([921600] * 8, 8).equal
+    with pytest.raises(ValueError):
+        multigpu.StitchLayout([921600] * 300, 8)      # > int32 header
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, points, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    R = oracle.restatement()
+    layout = multigpu.StitchLayout(points, world)
+    buf = multigpu.StitchedBuffer(layout, rank, "cpu")
+    for cam in buf.my_cams():
+        w, h = points[cam] // 8, 8
+        rec = R.frame(oracle.make_calib(w, h, translation=synth.D2C_BASELINE), synth.depth_frame(w, h, cam, 0),
+                      synth.color_frame(w, h, cam, 0), 3, w * 3, synth.TF_STITCH[cam % 8])
+        buf.slot(cam).copy_(torch.from_numpy(rec.reshape(-1).view(np.uint8).copy()))
+    buf.gather()
+    np.save(os.path.join(result_dir, "rank%d.npy" % rank), buf.wire_bytes().numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("points", [[512, 512, 512, 512], [512, 256, 1024, 64, 128]], ids=["equal", "ragged"])
+def test_two_rank_gloo_exchange_matches_reference_layout(tmp_path, points, restatement):
+    import oracle
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), points, str(tmp_path)), nprocs=world, join=True)
+    payloads = []
+    for cam, n in enumerate(points):
+        w, h = n // 8, 8
+        payloads.append(restatement.frame(oracle.make_calib(w, h, translation=synth.D2C_BASELINE),
+                                          synth.depth_frame(w, h, cam, 0), synth.color_frame(w, h, cam, 0), 3, w * 3,
+                                          synth.TF_STITCH[cam % 8]))
+    want = restatement.concat(payloads, 1)
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), "rank%d.npy" % r))
+        assert np.array_equal(got, want), "rank %d" % r
