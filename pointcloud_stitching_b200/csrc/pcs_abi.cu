@@ -295,7 +295,7 @@ int pcs_b200_create(const pcs_config *cfg, pcs_ctx **out) {
             pcs_b200_destroy(ctx);
             return fail(nullptr, PCS_ERR_CUDA, "cudaStreamCreate failed");
         }
-    int rc = pipe_configure(ctx->sm_count);
+    int rc = pipe_configure(ctx->device);
     if (rc != PCS_OK) {
         pcs_b200_destroy(ctx);
         return fail(nullptr, PCS_ERR_CUDA, "kernel attribute setup failed: %s",
@@ -398,9 +398,10 @@ int pcs_b200_send_xyzrgb_begin(pcs_ctx *ctx, int stream, const uint16_t *z16_hos
                                s.d_count, s.cs);
         if (rc < 0) return rc;
         CU(ctx, cudaMemcpyAsync(s.h_count, s.d_count, 4, cudaMemcpyDeviceToHost, s.cs));
-        // the count is only known on the device: copy the whole frame's worth, trim in end()
+        // the count is only known on the device: the records are copied out in end()
+    } else {
+        CU(ctx, cudaMemcpyAsync(dst, s.d_payload, (size_t)p.N * 10, cudaMemcpyDeviceToHost, s.cs));
     }
-    CU(ctx, cudaMemcpyAsync(dst, s.d_payload, (size_t)p.N * 10, cudaMemcpyDeviceToHost, s.cs));
     s.pending = true;
     s.pending_buffer = buffer_host;
     s.pending_header = write_header;
@@ -420,16 +421,15 @@ int pcs_b200_send_xyzrgb_end(pcs_ctx *ctx, int stream) {
     const int count = p.cutoff ? *s.h_count : p.N;
     const int size = 5 * count * (int)sizeof(int16_t);              // :697
     uint8_t *b = reinterpret_cast<uint8_t *>(s.pending_buffer);
+    if (p.cutoff && count > 0) {
+        CU(ctx, cudaMemcpyAsync(b + PCS_B200_HEADER_BYTES, s.d_payload, (size_t)size, cudaMemcpyDeviceToHost, s.cs));
+        CU(ctx, cudaStreamSynchronize(s.cs));
+    }
     // :673 memset(buffer, 0, BUF_SIZE) happens before packing: whatever the pack did not
     // overwrite inside the first 5 000 000 bytes is zero afterwards.
     const size_t zero_end = PCS_B200_CAMERA_BUF_SHORTS;             // bytes
     const size_t used_end = PCS_B200_HEADER_BYTES + (size_t)size;
-    if (used_end < zero_end) {
-        // with cutoff the D2H copied N records; everything past `count` is scratch, not output
-        const size_t copied_end = PCS_B200_HEADER_BYTES + (size_t)p.N * 10;
-        memset(b + used_end, 0, zero_end - used_end);
-        (void)copied_end;
-    }
+    if (used_end < zero_end) memset(b + used_end, 0, zero_end - used_end);
     memset(b, 0, PCS_B200_HEADER_BYTES);
     if (s.pending_header) memcpy(b, &size, sizeof(int));            // :715-718
     return size;

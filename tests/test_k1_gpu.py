@@ -227,6 +227,7 @@ def test_cutoff_compaction(ctx0, R, lane_reversed):
     assert size == len(want) * 10 and buf.view(np.int32)[0] == size
     assert np.array_equal(buf[2:2 + want.size].reshape(-1, 5), want)
     assert np.all(buf[2 + want.size:2500000] == 0)              # memset region past the records
+    assert np.all(buf[2500000:] == 0x5A5A)                      # nothing beyond BUF_SIZE bytes is touched
     got = ctx0.pack_from_vertices(3, xyz, uv, col)
     assert np.array_equal(got, want)
 

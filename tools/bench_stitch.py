@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the bench.py contract): stitch-side kernels and the voxel
+merge on one GPU, CUDA-event timed, inputs resident.  Writes gpurun_out/stitch_bench.json.
+
+    python tools/bench_stitch.py [--cams 4] [--iters 20]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import pointcloud_stitching_b200 as pcs  # noqa: E402
+from pointcloud_stitching_b200 import synth  # noqa: E402
+
+W, H = 1280, 720
+N = W * H
+
+
+def timed(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cams", type=int, default=4)
+    ap.add_argument("--iters", type=int, default=20)
+    a = ap.parse_args()
+    ctx = pcs.Context(device=0, max_streams=a.cams)
+    cs = torch.cuda.current_stream().cuda_stream
+    # realistic records: run K1 on synthetic frames, one camera each, into separate payloads
+    pays, jobs, keep = [], [], []
+    for c in range(a.cams):
+        ctx.set_stream(c, pcs.stream_desc(W, H, tf=synth.TF_STITCH[c % 8], translation=synth.D2C_BASELINE))
+        z = torch.from_numpy(synth.depth_frame(W, H, c, 0).view(np.int16)).cuda()
+        col = torch.from_numpy(synth.color_frame(W, H, c, 0)).cuda()
+        p = torch.zeros(N * 5, dtype=torch.int16, device="cuda")
+        keep.append((z, col))
+        pays.append(p)
+        jobs.append((c, z.data_ptr(), col.data_ptr(), p.data_ptr()))
+    b = ctx.batch(jobs)
+    b.run(cs)
+    torch.cuda.synchronize()
+    total = a.cams * N
+    st = torch.zeros(16 + total * 10, dtype=torch.uint8, device="cuda")
+    cloud = torch.zeros(total * 8, dtype=torch.float32, device="cuda")
+    ptrs, ns = [p.data_ptr() for p in pays], [N * 5] * a.cams
+    tfs = [synth.TF_STITCH[c % 8] for c in range(a.cams)]
+    res = {"cams": a.cams, "points": total}
+    for d in (1, 2, 4):
+        ms = timed(lambda: ctx.stitch_raw_dev(ptrs, ns, d, st.data_ptr() + 12, total * 10 + 4, cs), a.iters)
+        res["stitch_raw_d%d" % d] = {"ms": ms, "mpoints_s_in": total / ms / 1e3,
+                                     "GBps": (total * 10 / d + total * 10 / d) / ms / 1e6}
+    ms = timed(lambda: ctx.stitch_pcl_dev(ptrs, ns, 1, tfs, st.data_ptr() + 12, total * 10 + 4, None, cs), a.iters)
+    res["stitch_pcl"] = {"ms": ms, "mpoints_s": total / ms / 1e3, "GBps": total * 20 / ms / 1e6}
+    ms = timed(lambda: ctx.stitch_pcl_dev(ptrs, ns, 1, tfs, st.data_ptr() + 12, total * 10 + 4, cloud.data_ptr(), cs), a.iters)
+    res["stitch_pcl_cloud32"] = {"ms": ms, "mpoints_s": total / ms / 1e3, "GBps": total * 52 / ms / 1e6}
+    # voxel merge of the raw-stitched cloud (records at st+16)
+    ctx.stitch_raw_dev(ptrs, ns, 1, st.data_ptr() + 12, total * 10 + 4, cs)
+    out = torch.zeros(total * 5, dtype=torch.int16, device="cuda")
+    nv = [0]
+
+    def vox():
+        nv[0] = ctx.voxel_merge_dev(st.data_ptr() + 16, total, 10, out.data_ptr(), cs)
+    ms = timed(vox, max(3, a.iters // 4))
+    res["voxel_merge_10mm"] = {"ms": ms, "mpoints_s_in": total / ms / 1e3, "voxels": nv[0]}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "stitch_bench.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
