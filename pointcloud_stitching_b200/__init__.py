@@ -18,7 +18,8 @@ from . import synth  # noqa: F401  (synthetic frames + the reference's calibrati
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libpcs_b200.so")
+# PCS_B200_LIB: an alternative build of the same library (A/B experiments); default is the in-tree build
+LIB_PATH = os.environ.get("PCS_B200_LIB") or os.path.join(HERE, "libpcs_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "pcs_b200.h")
 
 RECORD_BYTES = 10
