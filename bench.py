@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--variant", type=int, default=0, help="kernel_variant: 0 auto, 1 direct, 2 pipelined")
     ap.add_argument("--tex", default="baseline", choices=["baseline", "aligned"],
                     help="depth->colour extrinsics: 15 mm baseline (D435-like) or identity")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: fused = K1 stores every tile to all peers (one kernel); nccl = K1 then all-gather")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -216,28 +218,43 @@ def main():
     S, F = args.streams, args.frames
     trans = synth.D2C_BASELINE if args.tex == "baseline" else (0.0, 0.0, 0.0)
 
-    ctx = pcs.Context(device=local, max_streams=S, kernel_variant=args.variant)
+    # ABI streams S..2S-1 mirror 0..S-1: the e2e leg double-buffers every camera (two frames in flight)
+    ctx = pcs.Context(device=local, max_streams=2 * S, kernel_variant=args.variant)
     for s in range(S):
         cam = rank * S + s
-        ctx.set_stream(s, pcs.stream_desc(W, H, tf=synth.TF_STITCH[cam % 8], translation=trans))
+        for k in (s, S + s):
+            ctx.set_stream(k, pcs.stream_desc(W, H, tf=synth.TF_STITCH[cam % 8], translation=trans))
 
     d_np, c_np = make_frames(S, F, rank)
     d_dev = torch.from_numpy(d_np.view(np.int16)).cuda()
     c_dev = torch.from_numpy(c_np).cuda()
     # stitched buffers, one per frame index: [pad 12][int32 bytes][world x S cameras x records]
+    from pointcloud_stitching_b200 import multigpu
     slot = S * NPTS * 10
-    stitched = [torch.zeros(16 + world * slot, dtype=torch.uint8, device="cuda") for _ in range(F)]
-    rec_views = [st[16:] for st in stitched]
-    for st in stitched:
-        st[12:16] = torch.from_numpy(np.frombuffer(np.int32(world * slot).tobytes(), np.uint8).copy()).cuda()
+    layout = multigpu.StitchLayout([NPTS] * (world * S), world)
+    exchange = "none" if world == 1 else args.exchange
+    sset = None
+    if exchange == "fused":
+        try:
+            sset = multigpu.SymmetricStitchedSet(layout, rank, torch.device("cuda", local), F)
+            stitched = sset.frames
+        except Exception as e:  # no symmetric memory on this box: say so and use the NCCL baseline
+            if rank == 0:
+                print("bench: symmetric memory unavailable (%r); falling back to --exchange nccl" % (e,), file=sys.stderr)
+            exchange = "nccl"
+    if sset is None:
+        stitched = [multigpu.StitchedBuffer(layout, rank, torch.device("cuda", local)) for _ in range(F)]
+    rec_views = [st.payload for st in stitched]
 
     def job(s, f):
-        pay = rec_views[f].data_ptr() + rank * slot + s * NPTS * 10
-        return (s, d_dev[s, f].data_ptr(), c_dev[s, f].data_ptr(), pay)
+        return (s, d_dev[s, f].data_ptr(), c_dev[s, f].data_ptr(), stitched[f].slot_ptr(rank * S + s))
 
     cs = torch.cuda.current_stream()
+    all_jobs = [job(s, f) for f in range(F) for s in range(S)]
     if world == 1:
-        batches = [ctx.batch([job(s, f) for f in range(F) for s in range(S)])]
+        batches = [ctx.batch(all_jobs)]
+    elif exchange == "fused":
+        batches = [ctx.batch_fanout(all_jobs, sset.local_base, sset.nbytes, sset.peer_bases)]
     else:
         batches = [ctx.batch([job(s, f) for s in range(S)]) for f in range(F)]
         comm = torch.cuda.Stream()
@@ -247,7 +264,10 @@ def main():
         if world == 1:
             batches[0].run(cs.cuda_stream)
             return
-        evs = []
+        if exchange == "fused":
+            batches[0].run(cs.cuda_stream)
+            sset.barrier()
+            return
         for f in range(F):
             batches[f].run(cs.cuda_stream)
             ev = torch.cuda.Event()
@@ -287,19 +307,24 @@ def main():
     pts_step = world * S * F * NPTS
     value = pts_step / (ms_step * 1e-3) / 1e6
 
-    # kernel-only timing of the fused kernel (for N > 1 the step also holds the all-gather)
+    # kernel-only timing of K1 without any exchange (for N > 1 the step above also moves the
+    # records over NVLink); this is what the HBM roofline refers to
+    local_batches = batches if world == 1 else [ctx.batch(all_jobs)]
+    for b in local_batches:
+        b.run(cs.cuda_stream)
     barrier()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record(cs)
     for _ in range(args.steps):
-        for b in batches:
+        for b in local_batches:
             b.run(cs.cuda_stream)
     k1.record(cs)
     torch.cuda.synchronize()
     ms_kernel_step = k0.elapsed_time(k1) / args.steps
-    launch_ms = ms_kernel_step / launches_per_step
+    launches_per_step_local = sum(b.launches for b in local_batches)
+    launch_ms = ms_kernel_step / launches_per_step_local
     peak, peak_src = measured_peak()
-    alg_bytes_launch = ALG_BYTES_PER_POINT * S * F * NPTS / launches_per_step
+    alg_bytes_launch = ALG_BYTES_PER_POINT * S * F * NPTS / launches_per_step_local
     achieved = alg_bytes_launch / (launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "k1_pipe" if args.variant != 1 else "k1_direct",
@@ -310,19 +335,25 @@ def main():
     if not args.no_e2e:
         hz = [[ctx.host_alloc(NPTS * 2, np.uint16) for _ in range(F)] for _ in range(S)]
         hc = [[ctx.host_alloc(NPTS * 3, np.uint8) for _ in range(F)] for _ in range(S)]
-        hb = [ctx.new_camera_buffer(pinned=True) for _ in range(S)]
+        hb = [[ctx.new_camera_buffer(pinned=True) for _ in range(S)] for _ in range(2)]
         for s in range(S):
             for f in range(F):
                 hz[s][f][:] = d_np[s, f].reshape(-1)
                 hc[s][f][:] = c_np[s, f].reshape(-1)
 
         def e2e_step():
+            # software pipeline: frame f of every camera is in flight while frame f-1 drains
             total = 0
             for f in range(F):
+                slot = f & 1
+                if f >= 2:
+                    for s in range(S):
+                        total += ctx.send_end(slot * S + s)
                 for s in range(S):
-                    ctx.send_begin(s, hz[s][f], hc[s][f], hb[s], True)
+                    ctx.send_begin(slot * S + s, hz[s][f], hc[s][f], hb[slot][s], True)
+            for f in range(max(0, F - 2), F):
                 for s in range(S):
-                    total += ctx.send_end(s)
+                    total += ctx.send_end((f & 1) * S + s)
             return total
 
         e2e_step()
@@ -341,7 +372,7 @@ def main():
         e2e = {"value": world * S * F * NPTS * n_e2e / dt / 1e6, "unit": "Mpoints/s",
                "h2d_bytes_per_step": S * F * NPTS * 5, "d2h_bytes_per_step": S * F * NPTS * 10,
                "api": "pcs_b200_send_xyzrgb_begin/_end (host z16+RGB8 in, reference camera buffer out), "
-                      "%d streams in flight, pinned host buffers" % S, "steps": n_e2e}
+                      "%d cameras x 2 frames in flight, pinned host buffers" % S, "steps": n_e2e}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -357,15 +388,22 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%d streams/GPU x %d frames x 1280x720 z16 depth + RGB8, fused deproject+transform+"
                                    "colour+pack (K1)%s; depth->colour extrinsics: %s" % (
-                                       S, F, "" if world == 1 else " + in-place NCCL all-gather of the packed records",
+                                       S, F, "" if world == 1 else (" + all-gather of the packed records fused into the kernel (peer TMA stores "
+                                                                  "over NVLink)" if exchange == "fused" else
+                                                                  " + in-place NCCL all-gather of the packed records"),
                                        "15 mm baseline" if args.tex == "baseline" else "identity"),
                        "streams_per_gpu": S, "frames_per_step": F, "points_per_step": pts_step,
                        "l2": "working set %.0f MB per step per GPU >> 126 MB L2 (no flush needed)" % (
                            ALG_BYTES_PER_POINT * S * F * NPTS / 1e6),
-                       "kernel_variant": args.variant, "tex": args.tex},
+                       "kernel_variant": args.variant, "tex": args.tex, "exchange": exchange},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
             "kernel_only": {"ms_per_step": ms_kernel_step, "mpoints_s_per_gpu": S * F * NPTS / (ms_kernel_step * 1e-3) / 1e6},
+            "nvlink": None if world == 1 else {
+                "recv_bytes_per_gpu_per_step": (world - 1) * slot * F,
+                "recv_GBps_per_gpu": (world - 1) * slot * F / (ms_step * 1e-3) / 1e9,
+                "note": "every GPU must receive (N-1)/N of the stitched cloud, 10 B/pt: this link rate, not HBM, "
+                        "bounds N > 1 (B200_PROFILING.md: 770 GB/s measured peer copy per direction)"},
         }
         print(json.dumps(line))
     if world > 1:

@@ -153,6 +153,16 @@ PCS_API int pcs_b200_pack_from_vertices(pcs_ctx *ctx, int stream, const float *x
 PCS_API int pcs_b200_batch_create(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs, pcs_batch **out);
 PCS_API int pcs_b200_batch_run(pcs_ctx *ctx, pcs_batch *batch, void *cuda_stream);
 PCS_API void pcs_b200_batch_destroy(pcs_ctx *ctx, pcs_batch *batch);
+/* Fused compute + exchange (multi-GPU stitch): like pcs_b200_batch_create, but every tile of
+ * records is stored by the same kernel to the local payload AND to the same offset of n_peers
+ * mirror buffers in peer GPU memory (peer-mapped pointers, e.g. CUDA IPC / symmetric memory),
+ * i.e. an all-gather of the packed XYZRGB records over NVLink with no second pass.  All
+ * payload_dev pointers must lie inside [local_base, local_base + local_bytes).  Replaces the
+ * TCP fan-in of readCloud (src/pcs-multicamera-client.cpp:363-371) + the concat (:385-395).
+ * The caller synchronises the ranks after batch_run before reading mirrored data. */
+PCS_API int pcs_b200_batch_create_fanout(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs,
+                                         const void *local_base, size_t local_bytes,
+                                         const void *const *peer_bases, int n_peers, pcs_batch **out);
 /* Number of kernel launches one batch_run issues (for launch accounting). */
 PCS_API int pcs_b200_batch_launches(const pcs_batch *batch);
 

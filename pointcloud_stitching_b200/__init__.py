@@ -116,6 +116,8 @@ def _load():
         "pcs_b200_pack_from_vertices": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp]),
         "pcs_b200_pack_from_vertices_dev": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]),
         "pcs_b200_batch_create": (C.c_int, [vp, C.POINTER(FrameJob), C.c_int, C.POINTER(vp)]),
+        "pcs_b200_batch_create_fanout": (C.c_int, [vp, C.POINTER(FrameJob), C.c_int, vp, C.c_size_t,
+                                                   C.POINTER(vp), C.c_int, C.POINTER(vp)]),
         "pcs_b200_batch_run": (C.c_int, [vp, vp, vp]),
         "pcs_b200_batch_destroy": (None, [vp, vp]),
         "pcs_b200_batch_launches": (C.c_int, [vp]),
@@ -238,14 +240,26 @@ class Context:
         return out[:cnt]
 
     # ---- camera side, batched / device resident
-    def batch(self, jobs):
-        """jobs: iterable of (stream, z16_ptr, color_ptr, payload_ptr[, xyzrgb_ptr[, count_ptr]])."""
+    @staticmethod
+    def _job_array(jobs):
         arr = (FrameJob * len(jobs))()
         for i, j in enumerate(jobs):
             j = tuple(j) + (None,) * (6 - len(j))
             arr[i] = FrameJob(j[0], 0, j[1], j[2], j[3], j[4], j[5])
+        return arr
+
+    def batch(self, jobs):
+        """jobs: iterable of (stream, z16_ptr, color_ptr, payload_ptr[, xyzrgb_ptr[, count_ptr]])."""
         h = C.c_void_p()
-        self._check(lib.pcs_b200_batch_create(self.handle, arr, len(jobs), C.byref(h)))
+        self._check(lib.pcs_b200_batch_create(self.handle, self._job_array(jobs), len(jobs), C.byref(h)))
+        return Batch(self, h)
+
+    def batch_fanout(self, jobs, local_base, local_bytes, peer_bases):
+        """Fused K1 + all-gather: records also go to the same offset of every peer mirror buffer."""
+        h = C.c_void_p()
+        peers = (C.c_void_p * max(1, len(peer_bases)))(*peer_bases)
+        self._check(lib.pcs_b200_batch_create_fanout(self.handle, self._job_array(jobs), len(jobs), local_base,
+                                                     local_bytes, peers, len(peer_bases), C.byref(h)))
         return Batch(self, h)
 
     def pack_from_vertices_dev(self, stream, xyz_ptr, uv_ptr, n, color_ptr, payload_ptr, count_ptr=None,

@@ -534,7 +534,8 @@ int pcs_b200_pack_from_vertices(pcs_ctx *ctx, int stream, const float *xyz_host,
 }
 
 // ---- camera side, batched ----------------------------------------------------
-int pcs_b200_batch_create(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs, pcs_batch **out) {
+static int batch_create_impl(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs, int n_peers,
+                             const long long *peer_delta, pcs_batch **out) {
     if (!ctx || !jobs || !out || n_jobs < 1 || n_jobs > 65535)
         return fail(ctx, PCS_ERR_INVALID, "bad batch arguments (1 <= n_jobs <= 65535)");
     *out = nullptr;
@@ -604,18 +605,47 @@ int pcs_b200_batch_create(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs, p
         if (ok) {
             std::vector<StreamParams> sp(ctx->max_streams);
             for (int i = 0; i < ctx->max_streams; ++i) sp[i] = ctx->streams[i].params;
-            int rc = pipe_build(b->pipe, b->jobs, sp, ctx->sm_count);
+            int rc = pipe_build(b->pipe, b->jobs, sp, ctx->sm_count, n_peers, peer_delta);
             if (rc == PCS_OK) b->use_pipe = true;
-            else if (ctx->kernel_variant == 2)
+            else if (ctx->kernel_variant == 2 || n_peers)
                 return bail(fail(ctx, rc, "pipelined kernel setup failed"));
-        } else if (ctx->kernel_variant == 2) {
+        } else if (ctx->kernel_variant == 2 || n_peers) {
             return bail(fail(ctx, PCS_ERR_UNSUPPORTED,
                              "kernel_variant=2 needs plain jobs (no cutoff / float output, aligned payloads)"));
         }
     }
+    if (n_peers && !b->use_pipe)
+        return bail(fail(ctx, PCS_ERR_UNSUPPORTED, "the fused exchange needs the pipelined kernel (kernel_variant != 1)"));
     b->launches = b->use_pipe ? pipe_launches(b->pipe) : (int)b->groups.size() + 3 * (int)b->cuts.size();
     *out = b;
     return PCS_OK;
+}
+
+int pcs_b200_batch_create(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs, pcs_batch **out) {
+    return batch_create_impl(ctx, jobs, n_jobs, 0, nullptr, out);
+}
+
+int pcs_b200_batch_create_fanout(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs,
+                                 const void *local_base, size_t local_bytes,
+                                 const void *const *peer_bases, int n_peers, pcs_batch **out) {
+    if (!ctx || !jobs || !out || !local_base || n_peers < 0 || n_peers > PIPE_MAX_PEERS || (n_peers && !peer_bases))
+        return fail(ctx, PCS_ERR_INVALID, "bad fan-out arguments (at most %d peers)", PIPE_MAX_PEERS);
+    long long delta[PIPE_MAX_PEERS] = {0};
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(local_base);
+    for (int p = 0; p < n_peers; ++p) {
+        if (!peer_bases[p] || (reinterpret_cast<uintptr_t>(peer_bases[p]) & 15) != (lo & 15))
+            return fail(ctx, PCS_ERR_INVALID, "peer %d: mirror base must share the local base's 16-byte alignment", p);
+        delta[p] = (long long)(reinterpret_cast<uintptr_t>(peer_bases[p]) - lo);
+    }
+    for (int j = 0; j < n_jobs; ++j) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(jobs[j].payload_dev);
+        int rc = check_stream(ctx, jobs[j].stream, true);
+        if (rc) return rc;
+        const size_t bytes = (size_t)ctx->streams[jobs[j].stream].params.N * 10;
+        if (a < lo || a + bytes > lo + local_bytes)
+            return fail(ctx, PCS_ERR_INVALID, "job %d: payload lies outside the mirrored buffer", j);
+    }
+    return batch_create_impl(ctx, jobs, n_jobs, n_peers, delta, out);
 }
 
 int pcs_b200_batch_run(pcs_ctx *ctx, pcs_batch *b, void *cuda_stream) {

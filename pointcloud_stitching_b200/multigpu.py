@@ -7,11 +7,16 @@ camera-index order behind an int32 byte count
 records straight into their slots of a replicated stitched buffer, so the "concat" is
 free, and the exchange is one collective over NVLink:
 
-* equal shards  -> ``all_gather_into_tensor`` in place (send = recv + rank * count);
-* ragged shards -> one ``broadcast`` per rank of that rank's slot (all-gather-v), e.g.
-  20 cameras on 8 GPUs = 3,3,3,3,2,2,2,2.
+* fused (the product path, :class:`SymmetricStitchedSet`): the stitched buffers live in
+  symmetric memory, every rank's K1 launch stores each tile of records to its own copy AND
+  to the same offset of every peer's copy (TMA bulk stores over NVLink,
+  ``pcs_b200_batch_create_fanout``), so the all-gather happens inside the compute kernel,
+  tile by tile, with no second pass; one device-side barrier ends the step;
+* NCCL baseline, equal shards  -> ``all_gather_into_tensor`` in place (send = recv + rank * count);
+* NCCL baseline, ragged shards -> one ``broadcast`` per rank of that rank's slot (all-gather-v),
+  e.g. 20 cameras on 8 GPUs = 3,3,3,3,2,2,2,2.
 
-torch.distributed is plumbing only (NCCL on GPUs, gloo in the CPU tests); no kernels here.
+torch.distributed is plumbing only (rendezvous, NCCL on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
 
@@ -99,3 +104,35 @@ class StitchedBuffer:
     def wire_bytes(self):
         """``[int32 bytes][records]`` exactly as the reference writes it to the viewer socket."""
         return self.raw[PAD - 4:]
+
+
+class SymmetricStitchedSet:
+    """``n_frames`` replicated stitched buffers in one symmetric-memory allocation, for the fused
+    K1 + exchange kernel.  ``local_base`` / ``nbytes`` / ``peer_bases`` are what
+    ``Context.batch_fanout`` takes; ``frames[f]`` are :class:`StitchedBuffer` views."""
+
+    def __init__(self, layout: StitchLayout, rank: int, device, n_frames: int, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.layout, self.rank, self.n_frames = layout, rank, n_frames
+        self.frame_bytes = (PAD + layout.total_bytes + 255) & ~255
+        self.nbytes = self.frame_bytes * n_frames
+        self.raw = symm.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.raw.zero_()
+        self.handle = symm.rendezvous(self.raw, group if group is not None else dist.group.WORLD)
+        ptrs = list(self.handle.buffer_ptrs)
+        self.local_base = self.raw.data_ptr()
+        assert ptrs[rank] == self.local_base
+        self.peer_bases = [p for r, p in enumerate(ptrs) if r != rank]
+        self.frames = []
+        for f in range(n_frames):
+            b = StitchedBuffer.__new__(StitchedBuffer)
+            b.layout, b.rank = layout, rank
+            b.raw = self.raw[f * self.frame_bytes:f * self.frame_bytes + PAD + layout.total_bytes]
+            b.payload = b.raw[PAD:]
+            hdr = np.frombuffer(np.int32(layout.total_bytes).tobytes(), np.uint8).copy()
+            b.raw[PAD - 4:PAD] = torch.from_numpy(hdr).to(device)
+            self.frames.append(b)
+
+    def barrier(self):
+        """Device-side barrier on the current stream: all ranks' fused launches have finished."""
+        self.handle.barrier()

@@ -1,0 +1,86 @@
+"""-m gpu, needs >= 2 GPUs (gpurun --gpus 2): one process per GPU over NCCL.  Both exchange paths
+-- the fused K1 + peer-store kernel (pcs_b200_batch_create_fanout) and the NCCL all-gather
+baseline -- must leave the reference's stitched layout, bit-exact against the oracle, on every rank."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+    pytest.skip("needs two CUDA devices", allow_module_level=True)
+
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+W, H = 256, 48
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, cams_total, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import pointcloud_stitching_b200 as pcs
+    from pointcloud_stitching_b200 import multigpu, synth
+    dev = torch.device("cuda", rank)
+    layout = multigpu.StitchLayout([W * H] * cams_total, world)
+    ctx = pcs.Context(device=rank, max_streams=cams_total)
+    n_frames = 2
+    sset = multigpu.SymmetricStitchedSet(layout, rank, dev, n_frames)
+    plain = [multigpu.StitchedBuffer(layout, rank, dev) for _ in range(n_frames)]
+    keep, jobs_fused, jobs_plain = [], [], []
+    for cam in layout.cams_of[rank]:
+        ctx.set_stream(cam, pcs.stream_desc(W, H, tf=synth.TF_STITCH[cam % 8], translation=synth.D2C_BASELINE))
+        for f in range(n_frames):
+            z = torch.from_numpy(synth.depth_frame(W, H, cam, f).view(np.int16)).to(dev)
+            c = torch.from_numpy(synth.color_frame(W, H, cam, f)).to(dev)
+            keep.append((z, c))
+            jobs_fused.append((cam, z.data_ptr(), c.data_ptr(), sset.frames[f].slot_ptr(cam)))
+            jobs_plain.append((cam, z.data_ptr(), c.data_ptr(), plain[f].slot_ptr(cam)))
+    cs = torch.cuda.current_stream().cuda_stream
+    # fused: one kernel computes and stores to every rank's mirror
+    bf = ctx.batch_fanout(jobs_fused, sset.local_base, sset.nbytes, sset.peer_bases)
+    sset.barrier()
+    bf.run(cs)
+    sset.barrier()
+    torch.cuda.synchronize()
+    # baseline: K1 then NCCL
+    bp = ctx.batch(jobs_plain)
+    bp.run(cs)
+    for f in range(n_frames):
+        plain[f].gather()
+    torch.cuda.synchronize()
+    for f in range(n_frames):
+        np.save(os.path.join(out_dir, "fused_r%d_f%d.npy" % (rank, f)), sset.frames[f].wire_bytes().cpu().numpy())
+        np.save(os.path.join(out_dir, "nccl_r%d_f%d.npy" % (rank, f)), plain[f].wire_bytes().cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cams_total", [4, 5], ids=["equal", "ragged"])
+def test_fused_and_nccl_exchange_match_oracle(tmp_path, cams_total):
+    import oracle
+    from pointcloud_stitching_b200 import synth
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), cams_total, str(tmp_path)), nprocs=world, join=True)
+    R = oracle.restatement()
+    cal = oracle.make_calib(W, H, translation=synth.D2C_BASELINE)
+    for f in range(2):
+        want = R.concat([R.frame(cal, synth.depth_frame(W, H, cam, f), synth.color_frame(W, H, cam, f), 3, W * 3,
+                                 synth.TF_STITCH[cam % 8]) for cam in range(cams_total)], 1)
+        for r in range(world):
+            for kind in ("fused", "nccl"):
+                got = np.load(os.path.join(str(tmp_path), "%s_r%d_f%d.npy" % (kind, r, f)))
+                assert np.array_equal(got, want), (kind, r, f)
