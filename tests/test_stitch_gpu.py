@@ -130,3 +130,38 @@ def test_voxel_merge_full_size_properties(ctx):
     assert np.all(np.diff(key) > 0)
     assert np.array_equal(ctx.voxel_merge(m, 10), m)
     assert len(m) == len(np.unique(np.floor_divide(rec[:, :3].astype(np.int32), 10), axis=0))
+
+
+@pytest.mark.parametrize("n_cams,w,h", [(4, 1280, 720), (20, 848, 480)], ids=["config3_4x720p", "config5_20x480p"])
+def test_baseline_configs_k1_concat_voxel(ctx, R, n_cams, w, h):
+    """BASELINE.json configs #3 / #5 on one GPU: every camera's K1 writes straight into its slot of
+    the stitched buffer (the concat costs nothing), then the 1 cm voxel merge runs on the stitched
+    records.  Compared with oracle deproject -> pack -> concat -> voxel merge, bit for bit."""
+    c2 = pcs.Context(device=0, max_streams=n_cams)
+    total = n_cams * w * h
+    st = torch.zeros(16 + total * 10, dtype=torch.uint8, device="cuda")
+    hdr = np.frombuffer(np.int32(total * 10).tobytes(), np.uint8).copy()
+    st[12:16] = torch.from_numpy(hdr).cuda()
+    jobs, keep, want_pay = [], [], []
+    cal = oracle.make_calib(w, h, translation=synth.D2C_BASELINE)
+    for cam in range(n_cams):
+        c2.set_stream(cam, pcs.stream_desc(w, h, tf=synth.TF_STITCH[cam % 8], translation=synth.D2C_BASELINE))
+        z, col = synth.depth_frame(w, h, cam, 0), synth.color_frame(w, h, cam, 0)
+        dz, dc = dev(z), dev(col)
+        keep.append((dz, dc))
+        jobs.append((cam, dz.data_ptr(), dc.data_ptr(), st.data_ptr() + 16 + cam * w * h * 10))
+        want_pay.append(R.frame(cal, z, col, 3, w * 3, synth.TF_STITCH[cam % 8]))
+    cs = torch.cuda.current_stream().cuda_stream
+    b = c2.batch(jobs)
+    b.run(cs)
+    torch.cuda.synchronize()
+    want_stitched = R.concat(want_pay, 1)
+    assert np.array_equal(st[12:].cpu().numpy(), want_stitched)
+    out = torch.zeros(total * 5, dtype=torch.int16, device="cuda")
+    nv = c2.voxel_merge_dev(st.data_ptr() + 16, total, 10, out.data_ptr(), cs)
+    torch.cuda.synchronize()
+    want_vox = R.voxel_merge(np.concatenate(want_pay), 10)
+    assert nv == len(want_vox)
+    assert np.array_equal(out[: nv * 5].cpu().numpy().reshape(-1, 5), want_vox)
+    b.close()
+    c2.close()
