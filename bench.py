@@ -49,6 +49,7 @@ def parse():
                     help="depth->colour extrinsics: 15 mm baseline (D435-like) or identity")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N > 1: fused = K1 stores every tile to all peers (one kernel); nccl = K1 then all-gather")
+    ap.add_argument("--e2e-depth", type=int, default=2, choices=[1, 2], help="frames in flight per camera in the e2e leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -342,8 +343,15 @@ def main():
                 hc[s][f][:] = c_np[s, f].reshape(-1)
 
         def e2e_step():
-            # software pipeline: frame f of every camera is in flight while frame f-1 drains
             total = 0
+            if args.e2e_depth == 1:
+                for f in range(F):
+                    for s in range(S):
+                        ctx.send_begin(s, hz[s][f], hc[s][f], hb[0][s], True)
+                    for s in range(S):
+                        total += ctx.send_end(s)
+                return total
+            # software pipeline: frame f of every camera is in flight while frame f-1 drains
             for f in range(F):
                 slot = f & 1
                 if f >= 2:
@@ -372,7 +380,7 @@ def main():
         e2e = {"value": world * S * F * NPTS * n_e2e / dt / 1e6, "unit": "Mpoints/s",
                "h2d_bytes_per_step": S * F * NPTS * 5, "d2h_bytes_per_step": S * F * NPTS * 10,
                "api": "pcs_b200_send_xyzrgb_begin/_end (host z16+RGB8 in, reference camera buffer out), "
-                      "%d cameras x 2 frames in flight, pinned host buffers" % S, "steps": n_e2e}
+                      "%d cameras x %d frame(s) in flight, pinned host buffers" % (S, args.e2e_depth), "steps": n_e2e}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
