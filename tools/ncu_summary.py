@@ -17,6 +17,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, launches, tag = sys.argv[1], sys.argv[2], sys.argv[3]
+name = sys.argv[4] if len(sys.argv) > 4 else "k1"
 out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
 
@@ -65,7 +66,7 @@ summary = {"source": os.path.basename(rep), "command": "ncu --set full --clock-c
            "dram_write_bytes_per_launch": sum(k["dram__bytes_write.sum"] for k in kernels) / len(kernels),
            "duration_us": sum(k["gpu__time_duration.sum"] for k in kernels) / len(kernels),
            "metrics_first_launch": k0}
-json.dump(summary, open(os.path.join(out, "%s_k1_ncu_summary.json" % tag), "w"), indent=1)
+json.dump(summary, open(os.path.join(out, "%s_%s_ncu_summary.json" % (tag, name)), "w"), indent=1)
 
 # ---- per-instruction stalls
 src = list(csv.reader(io.StringIO(ncu("--page", "source", "--csv", "--print-source", "sass"))))
@@ -79,7 +80,7 @@ for r in src[hi + 1:]:
         rows.append(r)
 tot = sum(int(r[h.index("# Samples")]) for r in rows)
 cols = ["stall_long_sb", "stall_short_sb", "stall_wait", "stall_mio", "stall_math", "stall_not_selected", "stall_selected"]
-with open(os.path.join(out, "%s_k1_stalls.md" % tag), "w") as f:
+with open(os.path.join(out, "%s_%s_stalls.md" % (tag, name)), "w") as f:
     f.write("# %s: warp-stall samples by SASS instruction, %s\n\n" % (tag, k0["kernel"]))
     f.write("%d instructions, %d samples (first captured launch).  Totals by reason:\n\n" % (len(rows), tot))
     for c in cols:
