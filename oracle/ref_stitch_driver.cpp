@@ -128,7 +128,7 @@ int ref_pcl_stitch_1cam(const int16_t *payload, int n_shorts, int ds, const floa
     if (ds < 1 || (n_shorts / 5) % ds) return -1;
     ensure_stitched_buf();
     downsample = ds;
-    std::memcpy(transform[0].m, tf16, 16 * sizeof(float));
+    std::memcpy(transform[0].data(), tf16, 16 * sizeof(float));
 #ifdef PCS_REF_CLIENT
     if (!pc_buf[0]) pc_buf[0] = (short *)malloc(sizeof(short) * 5000000);  // :554
 #endif

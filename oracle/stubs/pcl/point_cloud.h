@@ -6,7 +6,10 @@
 // spec in oracle/pcs_oracle.c (SPEC.md section 2); the viewer is a no-op.
 #pragma once
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -16,13 +19,22 @@ extern "C" {
 }
 
 namespace Eigen {
+// Storage lives OUT OF LINE, keyed by the object's address, and the object itself is empty.
+// Reason: both reference stitchers declare `Eigen::Matrix4f transform[NUM_CAMERAS]` with
+// NUM_CAMERAS == 1 and then assign transform[0..7] in main()
+// (src/pcs-multicamera-optimized.cpp:40,72,417-455) -- seven out-of-bounds objects.  With an
+// empty class those "objects" are just distinct addresses and filling them touches no memory
+// of the program, so the unmodified main() can run.
 struct Matrix4f {
-    float m[16];  // row-major
+    struct Store { float m[16]; };
+    static std::map<const void *, Store> &pool() { static std::map<const void *, Store> p; return p; }
+    float *data() { return pool()[this].m; }
+    const float *data() const { return pool()[this].m; }
     struct CommaInit {
         Matrix4f *self; int k;
-        CommaInit operator,(double v) { self->m[k] = (float)v; return CommaInit{self, k + 1}; }
+        CommaInit operator,(double v) { self->data()[k] = (float)v; return CommaInit{self, k + 1}; }
     };
-    CommaInit operator<<(double v) { m[0] = (float)v; return CommaInit{this, 1}; }
+    CommaInit operator<<(double v) { data()[0] = (float)v; return CommaInit{this, 1}; }
 };
 template <class T> using aligned_allocator = std::allocator<T>;
 }  // namespace Eigen
@@ -60,7 +72,7 @@ inline void transformPointCloud(const PointCloud<PointXYZRGB> &in, PointCloud<Po
                                 const Eigen::Matrix4f &t) {
     if (&in != &out) out = in;
     pcs_oracle_transform_cloud(reinterpret_cast<pcs_oracle_pclpoint *>(out.points.data()),
-                               (int)out.points.size(), t.m);
+                               (int)out.points.size(), t.data());
 }
 
 namespace visualization {
@@ -68,15 +80,36 @@ enum RenderingProperties { PCL_VISUALIZER_POINT_SIZE = 0 };
 template <class PointT> struct PointCloudColorHandlerRGBField {
     explicit PointCloudColorHandlerRGBField(const typename PointCloud<PointT>::Ptr &) {}
 };
+// The "viewer" is the hook the wire-protocol integration test observes the reference through:
+// run the unmodified stitcher with -v and every cloud handed to updatePointCloud() is appended to
+// $PCS_STUB_VIEWER_DUMP as [int32 n][n x 32-byte pcl::PointXYZRGB]; the window reports "stopped"
+// after $PCS_STUB_VIEWER_FRAMES updates (default: never), which makes runStitching() exit(0).
 class PCLVisualizer {
 public:
     explicit PCLVisualizer(const std::string &) {}
     void setBackgroundColor(double, double, double, int = 0) {}
     template <class C, class H> void addPointCloud(const C &, const H &, const std::string &) {}
     void setPointCloudRenderingProperties(int, double, const std::string &) {}
-    template <class C> void updatePointCloud(const C &, const std::string &) {}
+    template <class C> void updatePointCloud(const C &cloud, const std::string &) {
+        const char *path = getenv("PCS_STUB_VIEWER_DUMP");
+        if (path) {
+            FILE *f = fopen(path, "ab");
+            if (f) {
+                const int n = (int)cloud->points.size();
+                fwrite(&n, 4, 1, f);
+                fwrite(cloud->points.data(), sizeof(cloud->points[0]), (size_t)n, f);
+                fclose(f);
+            }
+        }
+        ++updates_;
+    }
     void spinOnce() {}
-    bool wasStopped() const { return true; }
+    bool wasStopped() const {
+        const char *lim = getenv("PCS_STUB_VIEWER_FRAMES");
+        return lim && updates_ >= atoi(lim);
+    }
+private:
+    int updates_ = 0;
 };
 }  // namespace visualization
 
