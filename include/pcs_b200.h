@@ -200,7 +200,9 @@ PCS_API int pcs_b200_stitch_pcl(pcs_ctx *ctx, const int16_t *const *payload_host
 
 /* Voxel-grid merge of n records (own integer specification, oracle/SPEC.md s3; the
  * reference includes pcl/filters/voxel_grid.h but never calls it).  Returns the
- * number of voxels written to out_dev (capacity n records). */
+ * number of voxels written to out_dev (capacity n records).  n * max(255, leaf_mm - 1)
+ * must stay below 2^32 (uint32 sums: n <= 16.8 M points at the 10 mm leaf).  The call
+ * synchronises cuda_stream once (the voxel count has to reach the host). */
 PCS_API int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
                              int16_t *out_dev, void *cuda_stream);
 PCS_API int pcs_b200_voxel_merge(pcs_ctx *ctx, const int16_t *records_host, int n, int leaf_mm,

@@ -155,9 +155,9 @@ class Batch:
         self.ctx._check(lib.pcs_b200_batch_run(self.ctx.handle, self.handle, C.c_void_p(cuda_stream)))
 
     def close(self):
-        if self.handle:
+        if self.handle and lib is not None and self.ctx.handle:
             lib.pcs_b200_batch_destroy(self.ctx.handle, self.handle)
-            self.handle = None
+        self.handle = None
 
     __del__ = close
 
@@ -176,7 +176,7 @@ class Context:
         self._pinned = []
 
     def close(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and lib is not None:   # lib is None at interpreter shutdown
             for p in self._pinned:
                 lib.pcs_b200_host_free(self.handle, p)
             self._pinned = []

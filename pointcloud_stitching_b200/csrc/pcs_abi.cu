@@ -186,6 +186,7 @@ int ensure_frame_buffers(pcs_ctx *ctx, StreamState &s) {
     const size_t n = (size_t)s.params.N, cb = (size_t)s.params.CH * s.params.stride;
     int rc;
     if (n > s.cap_pts) {
+        s.cap_pts = 0;   // a failed grow leaves null pointers: never trust the old capacity afterwards
         if ((rc = grow(ctx, s.d_z16, n))) return rc;
         if ((rc = grow(ctx, s.d_payload, n * 5))) return rc;
         if ((rc = grow(ctx, s.d_dense, n * 5))) return rc;
@@ -194,6 +195,7 @@ int ensure_frame_buffers(pcs_ctx *ctx, StreamState &s) {
         s.cap_pts = n;
     }
     if (cb > s.cap_color) {
+        s.cap_color = 0;
         if ((rc = grow(ctx, s.d_color, cb))) return rc;
         s.cap_color = cb;
     }
@@ -465,6 +467,7 @@ int pcs_b200_pack_from_vertices_dev(pcs_ctx *ctx, int stream, const float *xyz_d
     // -c needs scratch: ctx-owned, sized for n
     std::lock_guard<std::mutex> lk(s.mu);
     if ((size_t)n > s.cap_cut) {
+        s.cap_cut = 0;
         if ((rc = grow(ctx, s.d_cdense, (size_t)n * 5))) return rc;
         if ((rc = grow(ctx, s.d_ckeep, (size_t)n))) return rc;
         if ((rc = grow(ctx, s.d_ctiles, (size_t)n / CMP_TILE + 2))) return rc;
@@ -501,12 +504,14 @@ int pcs_b200_pack_from_vertices(pcs_ctx *ctx, int stream, const float *xyz_host,
     {
         std::lock_guard<std::mutex> lk(s.mu);
         if ((size_t)n > s.cap_vtx) {
+            s.cap_vtx = 0;
             if ((rc = grow(ctx, s.d_xyz, (size_t)n * 3))) return rc;
             if ((rc = grow(ctx, s.d_uv, (size_t)n * 2))) return rc;
             if ((rc = grow(ctx, s.d_vpayload, (size_t)n * 5))) return rc;
             s.cap_vtx = n;
         }
         if (cb > s.cap_color) {
+            s.cap_color = 0;
             if ((rc = grow(ctx, s.d_color, cb))) return rc;
             s.cap_color = cb;
         }
@@ -805,6 +810,9 @@ int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, in
     if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
     if (n < 0 || leaf_mm < 1 || leaf_mm > 32767 || (n && (!records_dev || !out_dev)))
         return fail(ctx, PCS_ERR_INVALID, "bad voxel-merge arguments");
+    // the per-voxel sums are uint32 (oracle/SPEC.md s3): 255 * n and (leaf - 1) * n must fit
+    if ((long long)n * 255 > 0xFFFFFFFFll || (long long)n * (leaf_mm - 1) > 0xFFFFFFFFll)
+        return fail(ctx, PCS_ERR_UNSUPPORTED, "voxel merge: n * max(255, leaf_mm - 1) must stay below 2^32");
     if (n == 0) return 0;
     CU(ctx, cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> lk(ctx->scratch_mu);
