@@ -85,6 +85,12 @@ CASES = {
     "720p_aligned": dict(w=1280, h=720),
     "720p_baseline": dict(w=1280, h=720, translation=synth.D2C_BASELINE),
     "720p_rotated": dict(w=1280, h=720, translation=(0.015, -0.002, 0.001), rotation=small_rotation()),
+    # a factory-calibration-sized rotation (~0.1 degree) and sub-millimetre y/z offsets: the windowed path
+    "720p_rot_small": dict(w=1280, h=720, translation=(0.0148, 0.0002, 0.0003),
+                           rotation=small_rotation(0.0015, -0.002, 0.001)),
+    "480p_rot_small": dict(w=848, h=480, translation=(0.0148, -0.0003, 0.0002),
+                           rotation=small_rotation(-0.002, 0.001, 0.0015)),
+    "720p_translate_yz": dict(w=1280, h=720, translation=(0.015, 0.0004, -0.0006)),
     "480p_aligned": dict(w=848, h=480),
     "480p_baseline": dict(w=848, h=480, translation=synth.D2C_BASELINE),
     "720p_color1080p": dict(w=1280, h=720, cw=1920, ch=1080, translation=synth.D2C_BASELINE),
@@ -100,7 +106,8 @@ CASES = {
 # what the bulk-async pipelined kernel accepts (pipe_supports, pcs_k1_pipe.cuh); for everything
 # else kernel_variant=2 must refuse loudly rather than fall back
 PIPELINED = {"720p_aligned", "720p_baseline", "480p_aligned", "480p_baseline", "small_64x4",
-             "small_128x6_baseline", "wide_2048x16_baseline"}
+             "small_128x6_baseline", "wide_2048x16_baseline", "720p_rot_small", "480p_rot_small",
+             "720p_translate_yz", "720p_color1080p"}
 
 
 @pytest.mark.parametrize("case", list(CASES))
@@ -128,6 +135,19 @@ def test_fused_kernel_vs_oracle(ctx, R, case):
         assert rec.shape == want.shape
         bad = np.nonzero((rec != want).any(axis=1))[0]
         assert bad.size == 0, "first mismatches at points %s: got %s want %s" % (bad[:5], rec[bad[:5]], want[bad[:5]])
+
+
+def test_windowed_taps_fall_back_to_global_loads(ctx, R):
+    """Very near depths under a rotated calibration: most taps land outside the staged colour-row
+    window (and many are clamped at the image border); the result must not change."""
+    w, h = 1280, 720
+    kw = dict(translation=(0.0148, 0.0002, 0.0003), rotation=small_rotation(0.0015, -0.002, 0.001))
+    cal, desc = calib_and_desc(w, h, tf=synth.TF_STITCH[3], **kw)
+    ctx.set_stream(1, desc)
+    z = synth.depth_frame(w, h, 8, 8, lo=1, hi=120)
+    col = synth.color_frame(w, h, 8, 8)
+    (rec, _, _), = run_batch(ctx, [(1, z, col)], None)
+    assert np.array_equal(rec, R.frame(cal, z, col, 3, w * 3, synth.TF_STITCH[3]))
 
 
 def test_extreme_depths(ctx, R):
