@@ -725,9 +725,30 @@ static int stitch_common(pcs_ctx *ctx, const int16_t *const *payload_dev, const 
     tab.out_off[n_cams] = (int)total;
     if ((size_t)total * 10 + 4 > cap) return fail(ctx, PCS_ERR_CAPACITY, "stitched buffer too small: need %lld bytes", total * 10 + 4);
     CU(ctx, cudaSetDevice(ctx->device));
-    const int blocks = std::max(1, (int)((total + 255) / 256));
-    if (pcl) stitch_kernel<true><<<blocks, 256, 0, cs>>>(tab, tfs, stitched_dev, (float4 *)cloud32_dev);
-    else stitch_kernel<false><<<blocks, 256, 0, cs>>>(tab, tfs, stitched_dev, nullptr);
+    // vectorised path: no decimation, whole octets per camera, 16-byte aligned everywhere, and
+    // (PCL) coordinates that stay far inside int32 so that cvt.rzi == x86 cvttss2si
+    bool vec = downsample == 1 && !cloud32_dev && total > 0 &&
+               ((reinterpret_cast<uintptr_t>(stitched_dev) + 4) & 15) == 0;
+    VecTable vt{};
+    vt.one = 1.0f;
+    for (int i = 0; i < n_cams && vec; ++i) {
+        vec = tab.n_in[i] % 8 == 0 && (reinterpret_cast<uintptr_t>(tab.src[i]) & 15) == 0;
+        vt.tile_off[i + 1] = vt.tile_off[i] + (tab.n_in[i] / 8 + 31) / 32;
+        if (pcl)
+            for (int r = 0; r < 3 && vec; ++r) {
+                const float *m = tfs.m[i] + 4 * r;
+                vec = (std::fabs(m[0]) + std::fabs(m[1]) + std::fabs(m[2])) * 32.768f + std::fabs(m[3]) < 2.0e6f;
+            }
+    }
+    if (vec) {
+        const int blocks = (vt.tile_off[n_cams] + 7) / 8;
+        if (pcl) stitch_vec<true><<<blocks, 256, 0, cs>>>(tab, tfs, vt, stitched_dev);
+        else stitch_vec<false><<<blocks, 256, 0, cs>>>(tab, tfs, vt, stitched_dev);
+    } else {
+        const int blocks = std::max(1, (int)((total + 255) / 256));
+        if (pcl) stitch_kernel<true><<<blocks, 256, 0, cs>>>(tab, tfs, stitched_dev, (float4 *)cloud32_dev);
+        else stitch_kernel<false><<<blocks, 256, 0, cs>>>(tab, tfs, stitched_dev, nullptr);
+    }
     CU(ctx, cudaGetLastError());
     return (int)(total * 10);
 }

@@ -328,4 +328,94 @@ stitch_kernel(const __grid_constant__ CamTable tab, const __grid_constant__ TfTa
     }
 }
 
+// ---------------------------------------------------------------------------
+// Vectorised stitch for the common case (no decimation, whole octets per camera, 16-byte
+// aligned source and destination): a warp moves 32 octets = 2560 contiguous bytes with
+// coalesced 16-byte loads and stores; for the PCL path the records take a round trip through
+// shared memory so that each lane can unpack / transform / repack its own eight records
+// with packed fp32x2 arithmetic.  Same bits as stitch_kernel (tests compare both with the oracle).
+struct VecTable {
+    int32_t tile_off[MAX_CAMS + 1];   // exclusive prefix of warp tiles (32 octets) per camera
+    float one;                        // opaque 1.0f (see pcs_k1_pipe.cuh on FFMA2 contraction)
+};
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+template <bool PCL>
+__global__ void __launch_bounds__(256)
+stitch_vec(const __grid_constant__ CamTable tab, const __grid_constant__ TfTable tfs,
+           const __grid_constant__ VecTable vt, uint8_t *__restrict__ stitched) {
+    __shared__ uint4 slabs[8][32 * 5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * 8 + warp;
+    const int total = tab.out_off[tab.n_cams];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<int32_t *>(stitched) = total * 10;
+    if (tile >= vt.tile_off[tab.n_cams]) return;
+    int c = 0;
+    while (c + 1 < tab.n_cams && tile >= vt.tile_off[c + 1]) ++c;
+    const int oct0 = (tile - vt.tile_off[c]) * 32;                 // first octet of this tile in camera c
+    const int valid = min(32, tab.n_in[c] / 8 - oct0);             // octets in this tile
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(tab.src[c]) + (size_t)oct0 * 80;
+    uint8_t *dst = stitched + 4 + ((size_t)tab.out_off[c] + (size_t)oct0 * 8) * 10;
+    const int n16 = valid * 5;
+    uint4 *slab = slabs[warp];
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (k * 32 + lane < n16) slab[k * 32 + lane] = ld_global_nc_v4(src + (size_t)(k * 32 + lane) * 16);
+    __syncwarp();
+    if (PCL && lane < valid) {
+        uint32_t w[20];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const uint4 v = slab[lane * 5 + k];
+            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+        }
+        const float *m = tfs.m[c];
+        const float2 one = f2(vt.one, vt.one), k1000 = f2(1000.f, 1000.f), rk = f2(1.0f / 1000.0f, 1.0f / 1000.0f),
+                     nk = f2(-1000.f, -1000.f);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            // records A = 2p, B = 2p+1 in words w[5p .. 5p+4]
+            const uint32_t w0 = w[5 * p], w1 = w[5 * p + 1], w2 = w[5 * p + 2], w3 = w[5 * p + 3], w4 = w[5 * p + 4];
+            float2 c3[3];
+            c3[0] = f2((float)(int16_t)(w0 & 0xFFFF), (float)(int16_t)(w2 >> 16));
+            c3[1] = f2((float)(int16_t)(w0 >> 16), (float)(int16_t)(w3 & 0xFFFF));
+            c3[2] = f2((float)(int16_t)(w1 & 0xFFFF), (float)(int16_t)(w3 >> 16));
+            // src/pcs-multicamera-optimized.cpp:237-239: x = (float)s / 1000.0f -- division by a constant
+            // with the correctly rounded reciprocal and two Markstein corrections (see pcs_k1_pipe.cuh)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float2 u0 = __fmul2_rn(c3[a], rk);
+                const float2 r0 = __ffma2_rn(nk, u0, c3[a]);
+                const float2 u1 = __ffma2_rn(r0, rk, u0);
+                const float2 r1 = __ffma2_rn(nk, u1, c3[a]);
+                c3[a] = __ffma2_rn(r1, rk, u1);
+            }
+            uint32_t o[3][2];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                // oracle/SPEC.md s2: ((m0*x + m1*y) + m2*z) + m3, no contraction
+                float2 acc = __ffma2_rn(__fmul2_rn(f2(m[4 * r], m[4 * r]), c3[0]), one,
+                                        __fmul2_rn(f2(m[4 * r + 1], m[4 * r + 1]), c3[1]));
+                acc = __ffma2_rn(acc, one, __fmul2_rn(f2(m[4 * r + 2], m[4 * r + 2]), c3[2]));
+                acc = __ffma2_rn(acc, one, f2(m[4 * r + 3], m[4 * r + 3]));
+                const float2 mm = __fmul2_rn(acc, k1000);          // :255-257
+                o[r][0] = (uint32_t)__float2int_rz(mm.x);
+                o[r][1] = (uint32_t)__float2int_rz(mm.y);
+            }
+            w[5 * p] = __byte_perm(o[0][0], o[1][0], 0x5410);
+            w[5 * p + 1] = __byte_perm(o[2][0], w1, 0x7610);                    // keep rg of record A
+            w[5 * p + 2] = __byte_perm(w2 & 0xFF, o[0][1], 0x5410);             // b & 0xFF (:242), x of record B
+            w[5 * p + 3] = __byte_perm(o[1][1], o[2][1], 0x5410);
+            w[5 * p + 4] = w4 & 0x00FFFFFFu;                                    // rg, b & 0xFF of record B
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) slab[lane * 5 + k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (k * 32 + lane < n16) st_global_v4(dst + (size_t)(k * 32 + lane) * 16, slab[k * 32 + lane]);
+}
+
 }  // namespace pcs

@@ -10,7 +10,7 @@
 
 int main(void)
 {
-    static const float widths[] = {8, 24, 64, 96, 128, 256, 320, 424, 480, 640, 720, 848, 1024, 1080, 1280, 1920, 2048, 3840};
+    static const float widths[] = {1000 /* CONV_RATE of the stitcher's unpack */, 8, 24, 64, 96, 128, 256, 320, 424, 480, 640, 720, 848, 1024, 1080, 1280, 1920, 2048, 3840};
     long long bad = 0, total = 0;
     for (unsigned wi = 0; wi < sizeof widths / sizeof *widths; ++wi) {
         const float b = widths[wi], y = 1.0f / b, nb = -b;

@@ -67,6 +67,27 @@ def test_multi_camera_vs_oracle(ctx, R, n_cams, downsample):
     assert np.array_equal(ctx.stitch_pcl(pay, tfs, downsample), R.pcl_stitch(pay, tfs, downsample))
 
 
+@pytest.mark.parametrize("sizes", [[921600, 407040, 8, 256 * 77], [8], [264, 0, 2048]])
+def test_vectorised_path_vs_oracle(ctx, R, sizes):
+    """No decimation, whole octets per camera, aligned buffers: the warp-tiled 16-byte path
+    (stitch_vec) -- every int16 value, every colour byte, against the oracle."""
+    rng = np.random.default_rng(len(sizes))
+    pay = [random_records(rng, n) for n in sizes]
+    pay[0][:65536 if sizes[0] >= 65536 else sizes[0], 0] = np.arange(-32768, 32768)[: min(65536, sizes[0])]
+    tfs = [synth.TF_STITCH[(k + 3) % 8] for k in range(len(sizes))]
+    d = [dev(p.reshape(-1)) if p.size else torch.zeros(8, dtype=torch.int16, device="cuda") for p in pay]
+    total = sum(sizes)
+    st = torch.zeros(total * 10 + 32, dtype=torch.uint8, device="cuda")
+    cs = torch.cuda.current_stream().cuda_stream
+    size = ctx.stitch_raw_dev([t.data_ptr() for t in d], [p.size for p in pay], 1, st.data_ptr() + 12, total * 10 + 4, cs)
+    torch.cuda.synchronize()
+    assert np.array_equal(st[12:12 + size + 4].cpu().numpy(), R.concat(pay, 1))
+    size = ctx.stitch_pcl_dev([t.data_ptr() for t in d], [p.size for p in pay], 1, tfs, st.data_ptr() + 12,
+                              total * 10 + 4, None, cs)
+    torch.cuda.synchronize()
+    assert np.array_equal(st[12:12 + size + 4].cpu().numpy(), R.pcl_stitch(pay, tfs, 1))
+
+
 def test_device_path_and_cloud32(ctx, R):
     rng = np.random.default_rng(5)
     pay = [random_records(rng, n) for n in (921600, 407040, 8, 123457)]
