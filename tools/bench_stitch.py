@@ -36,7 +36,7 @@ def timed(fn, iters):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cams", type=int, default=4)
+    ap.add_argument("--cams", type=int, default=16, help="16 x 720p = 147 MB in + 147 MB out: larger than the 126 MB L2")
     ap.add_argument("--iters", type=int, default=20)
     a = ap.parse_args()
     ctx = pcs.Context(device=0, max_streams=a.cams)
