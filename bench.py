@@ -287,10 +287,15 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    # A step is ~0.2 ms, so the timed region is a few milliseconds: keep the GPU busy with the same
+    # work for ~0.5 s first (clocks ramped, nvidia-smi gets samples under load), then time K steps
+    # back to back with that load; the sampler runs across both.
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+    ramp_steps = max(1, int(0.5 / 0.0002)) if world == 1 else 60
+    for _ in range(ramp_steps):
+        step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(cs)
