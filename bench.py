@@ -287,13 +287,14 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    # A step is ~0.2 ms, so the timed region is a few milliseconds: keep the GPU busy with the same
-    # work for ~0.5 s first (clocks ramped, nvidia-smi gets samples under load), then time K steps
-    # back to back with that load; the sampler runs across both.
+    # A step is ~0.2 ms, so the timed region is a few milliseconds, shorter than nvidia-smi's
+    # sampling period: keep the GPU busy with the same work for ~0.15 s first (a couple of clock
+    # samples under this very load), then time K steps back to back; the sampler runs across both.
+    # (A much longer ramp -- 0.5 s -- runs this 1 kW part into sw_power_cap at ~1870 MHz, -8 %.)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ramp_steps = max(1, int(0.5 / 0.0002)) if world == 1 else 60
+    ramp_steps = max(1, int(0.15 / 0.0002)) if world == 1 else 30
     for _ in range(ramp_steps):
         step()
     barrier()
@@ -328,7 +329,9 @@ def main():
     torch.cuda.synchronize()
     ms_kernel_step = k0.elapsed_time(k1) / args.steps
     launches_per_step_local = sum(b.launches for b in local_batches)
-    launch_ms = ms_kernel_step / launches_per_step_local
+    # roofline: the dominant kernel's launch time over the timed region itself at N = 1 (a step IS
+    # one k1_pipe launch there); for N > 1 the step also holds the exchange, so the K1-only loop
+    launch_ms = (ms_step if world == 1 else ms_kernel_step) / launches_per_step_local
     peak, peak_src = measured_peak()
     alg_bytes_launch = ALG_BYTES_PER_POINT * S * F * NPTS / launches_per_step_local
     achieved = alg_bytes_launch / (launch_ms * 1e-3) / 1e9
