@@ -457,9 +457,9 @@ int pcs_b200_pack_from_vertices_dev(pcs_ctx *ctx, int stream, const float *xyz_d
     StreamState &s = ctx->streams[stream];
     cudaStream_t cs = (cudaStream_t)cuda_stream;
     CU(ctx, cudaSetDevice(ctx->device));
-    const int blocks = (n + 255) / 256;
+    const int blocks = (n / 4 + K1A_THREADS - 1) / K1A_THREADS;
     if (!s.params.cutoff) {
-        k1a_vertices<false><<<blocks, 256, 0, cs>>>(xyz_dev, uv_dev, n, color_dev, ctx->d_params,
+        k1a_vertices<false><<<blocks, K1A_THREADS, 0, cs>>>(xyz_dev, uv_dev, n, color_dev, ctx->d_params,
                                                     stream, payload_dev, nullptr);
         CU(ctx, cudaGetLastError());
         return n;
@@ -481,7 +481,7 @@ int pcs_b200_pack_from_vertices_dev(pcs_ctx *ctx, int stream, const float *xyz_d
         }
         count_dev = s.d_count;
     }
-    k1a_vertices<true><<<blocks, 256, 0, cs>>>(xyz_dev, uv_dev, n, color_dev, ctx->d_params, stream,
+    k1a_vertices<true><<<blocks, K1A_THREADS, 0, cs>>>(xyz_dev, uv_dev, n, color_dev, ctx->d_params, stream,
                                                s.d_cdense, s.d_ckeep);
     CU(ctx, cudaGetLastError());
     rc = launch_compaction(ctx, s.d_ckeep, s.d_cdense, n, s.params.lane_rev, s.d_ctiles, payload_dev,

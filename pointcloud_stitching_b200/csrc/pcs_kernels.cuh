@@ -117,41 +117,85 @@ k1_direct(const DevJob *__restrict__ jobs, const StreamParams *__restrict__ stre
 }
 
 // ---------------------------------------------------------------------------
-// K1a: same inputs as the reference function.  One point per thread; a warp's 32
-// records (320 B) are staged in shared memory and leave as 16-byte stores.
+// K1a: same inputs as the reference function.  One group of FOUR points per thread (the
+// reference's own SIMD group; n % 4 == 0 is its precondition too): the group's vertices are
+// 48 contiguous bytes and its tex coords 32, i.e. five 16-byte loads; the four records (40 B)
+// go through a per-warp shared-memory slab and leave as coalesced 16-byte stores.
+constexpr int K1A_THREADS = 256;
+
 template <bool CUTOFF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(K1A_THREADS)
 k1a_vertices(const float *__restrict__ xyz, const float *__restrict__ uv, int n,
              const uint8_t *__restrict__ color, const StreamParams *__restrict__ streams, int stream,
              int16_t *__restrict__ out, uint8_t *__restrict__ keep) {
-    __shared__ __align__(16) uint16_t slabs[8][32 * 5];
-    const StreamParams &sp = streams[stream];
+    __shared__ __align__(16) uint2 slabs[K1A_THREADS / 32][32 * 5];   // 32 groups x 40 B per warp
+    __shared__ StreamParams sp;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(streams + stream);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&sp);
+        for (int i = threadIdx.x; i < (int)(sizeof(StreamParams) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int warp_i0 = i - lane;
-    if (warp_i0 >= n) return;
-    if (i < n) {
-        const float p0 = __ldg(xyz + 3 * (size_t)i), p1 = __ldg(xyz + 3 * (size_t)i + 1),
-                    p2 = __ldg(xyz + 3 * (size_t)i + 2);
-        const float u = __ldg(uv + 2 * (size_t)i), v = __ldg(uv + 2 * (size_t)i + 1);
-        const int xi = tex_to_pixel(u, sp.cwf, sp.CW - 1);
-        const int yi = tex_to_pixel(v, sp.chf, sp.CH - 1);
-        const uint32_t rgb = load_rgb(color, xi * sp.bpp + yi * sp.stride);
-        const Rec r = make_record(sp.tf, p0, p1, p2, rgb);
-        uint16_t *s = slabs[warp] + lane * 5;
-        s[0] = (uint16_t)r.a; s[1] = (uint16_t)(r.a >> 16);
-        s[2] = (uint16_t)r.b; s[3] = (uint16_t)(r.b >> 16);
-        s[4] = (uint16_t)r.c;
-        if (CUTOFF) keep[i] = cutoff_keep(sp, p0, p2) ? 1 : 0;
+    const int groups = n >> 2;
+    const int gidx = blockIdx.x * blockDim.x + threadIdx.x;     // group index
+    const int warp_g0 = gidx - lane;
+    if (warp_g0 >= groups) return;
+    const bool vec_in = ((reinterpret_cast<uintptr_t>(xyz) | reinterpret_cast<uintptr_t>(uv)) & 15) == 0;
+    if (gidx < groups) {
+        float p[12], t[8];
+        if (vec_in) {
+            const uint4 *x4 = reinterpret_cast<const uint4 *>(xyz) + 3 * (size_t)gidx;
+            const uint4 *u4 = reinterpret_cast<const uint4 *>(uv) + 2 * (size_t)gidx;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint4 v = ld_global_nc_v4(x4 + k);
+                p[4 * k] = __uint_as_float(v.x); p[4 * k + 1] = __uint_as_float(v.y);
+                p[4 * k + 2] = __uint_as_float(v.z); p[4 * k + 3] = __uint_as_float(v.w);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint4 v = ld_global_nc_v4(u4 + k);
+                t[4 * k] = __uint_as_float(v.x); t[4 * k + 1] = __uint_as_float(v.y);
+                t[4 * k + 2] = __uint_as_float(v.z); t[4 * k + 3] = __uint_as_float(v.w);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) p[k] = __ldg(xyz + 12 * (size_t)gidx + k);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = __ldg(uv + 8 * (size_t)gidx + k);
+        }
+        Rec r[4];
+        uint32_t kp = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xi = tex_to_pixel(t[2 * k], sp.cwf, sp.CW - 1);
+            const int yi = tex_to_pixel(t[2 * k + 1], sp.chf, sp.CH - 1);
+            const uint32_t rgb = load_rgb(color, xi * sp.bpp + yi * sp.stride);
+            r[k] = make_record(sp.tf, p[3 * k], p[3 * k + 1], p[3 * k + 2], rgb);
+            if (CUTOFF) kp |= (cutoff_keep(sp, p[3 * k], p[3 * k + 2]) ? 1u : 0u) << (8 * k);
+        }
+        if (CUTOFF) reinterpret_cast<uint32_t *>(keep)[gidx] = kp;
+        uint32_t w[10];
+        pack_pair(r[0], r[1], w);
+        pack_pair(r[2], r[3], w + 5);
+        uint2 *s2 = slabs[warp] + lane * 5;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) s2[k] = make_uint2(w[2 * k], w[2 * k + 1]);
     }
     __syncwarp();
-    const int valid = min(32, n - warp_i0);
-    uint8_t *dst = reinterpret_cast<uint8_t *>(out) + (size_t)warp_i0 * 10;
-    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && valid == 32) {
-        if (lane < 20) st_global_v4(dst + lane * 16, reinterpret_cast<const uint4 *>(slabs[warp])[lane]);
+    const int valid = min(32, groups - warp_g0);                 // groups in this warp
+    uint8_t *dst = reinterpret_cast<uint8_t *>(out) + (size_t)warp_g0 * 40;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (valid * 40) % 16 == 0) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(slabs[warp]);
+        const int n16 = valid * 40 / 16;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (k * 32 + lane < n16) st_global_v4(dst + (size_t)(k * 32 + lane) * 16, s4[k * 32 + lane]);
     } else {
+        const uint16_t *s16 = reinterpret_cast<const uint16_t *>(slabs[warp]);
         uint16_t *d16 = reinterpret_cast<uint16_t *>(dst);
-        for (int c = lane; c < valid * 5; c += 32) d16[c] = slabs[warp][c];
+        for (int c = lane; c < valid * 20; c += 32) d16[c] = s16[c];
     }
 }
 

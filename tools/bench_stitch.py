@@ -77,6 +77,15 @@ def main():
         nv[0] = ctx.voxel_merge_dev(st.data_ptr() + 16, total, 10, out.data_ptr(), cs)
     ms = timed(vox, max(3, a.iters // 4))
     res["voxel_merge_10mm"] = {"ms": ms, "mpoints_s_in": total / ms / 1e3, "voxels": nv[0]}
+    # K1a: the reference seam itself (vertices + tex coords in), 8 frames of 1280x720 per call
+    nf = 8
+    xyz = torch.randn(nf * N, 3, device="cuda") * 2.0
+    uv = torch.rand(nf * N, 2, device="cuda")
+    col = keep[0][1]
+    pay1 = torch.zeros(nf * N * 5, dtype=torch.int16, device="cuda")
+    ms = timed(lambda: ctx.pack_from_vertices_dev(0, xyz.data_ptr(), uv.data_ptr(), nf * N, col.data_ptr(),
+                                                  pay1.data_ptr(), None, cs), a.iters)
+    res["k1a_from_vertices"] = {"ms": ms, "mpoints_s": nf * N / ms / 1e3, "GBps": nf * N * 30 / ms / 1e6}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "stitch_bench.json"), "w") as f:
         json.dump(res, f, indent=1)
