@@ -86,7 +86,7 @@ typedef struct pcs_config {
     int32_t device;            /* CUDA device ordinal */
     int32_t max_streams;       /* camera streams this context serves (>= 1) */
     int32_t kernel_variant;    /* 0 = auto, 1 = direct (LDG/STG), 2 = bulk-async pipelined (TMA) */
-    int32_t reserved;
+    int32_t voxel_variant;     /* 0 = auto, 1 = (key, index) pair sort, 2 / 3 = one-sweep sort, 8- / 10-bit digits */
 } pcs_config;
 
 /* One frame of work for the batched device-resident path. */

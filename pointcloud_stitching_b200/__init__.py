@@ -51,7 +51,7 @@ class StreamDesc(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_streams", C.c_int32), ("kernel_variant", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("voxel_variant", C.c_int32)]
 
 
 class FrameJob(C.Structure):
@@ -165,8 +165,8 @@ class Batch:
 class Context:
     """pcs_ctx: one per process per GPU."""
 
-    def __init__(self, device=0, max_streams=8, kernel_variant=0):
-        cfg = Config(device, max_streams, kernel_variant, 0)
+    def __init__(self, device=0, max_streams=8, kernel_variant=0, voxel_variant=0):
+        cfg = Config(device, max_streams, kernel_variant, voxel_variant)
         h = C.c_void_p()
         rc = lib.pcs_b200_create(C.byref(cfg), C.byref(h))
         if rc != 0:

@@ -16,6 +16,7 @@
 #include "pcs_kernels.cuh"
 #include "pcs_k1_pipe.cuh"
 #include "pcs_voxel.cuh"
+#include "pcs_voxel_sweep.cuh"
 
 using namespace pcs;
 
@@ -62,6 +63,7 @@ struct pcs_ctx {
     int device = 0;
     int max_streams = 0;
     int kernel_variant = 0;
+    int voxel_variant = 0;
     int sm_count = 0;
     StreamState *streams = nullptr;
     StreamParams *d_params = nullptr;
@@ -286,6 +288,7 @@ int pcs_b200_create(const pcs_config *cfg, pcs_ctx **out) {
     ctx->device = cfg->device;
     ctx->max_streams = cfg->max_streams;
     ctx->kernel_variant = cfg->kernel_variant;
+    ctx->voxel_variant = cfg->voxel_variant;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->streams = new StreamState[cfg->max_streams];
     if (cudaMalloc(&ctx->d_params, sizeof(StreamParams) * cfg->max_streams) != cudaSuccess) {
@@ -298,6 +301,7 @@ int pcs_b200_create(const pcs_config *cfg, pcs_ctx **out) {
             return fail(nullptr, PCS_ERR_CUDA, "cudaStreamCreate failed");
         }
     int rc = pipe_configure(ctx->device);
+    if (rc == PCS_OK && (sweep_configure<8, 256, 16>() != 0 || sweep_configure<10, 256, 16>() != 0)) rc = PCS_ERR_CUDA;
     if (rc != PCS_OK) {
         pcs_b200_destroy(ctx);
         return fail(nullptr, PCS_ERR_CUDA, "kernel attribute setup failed: %s",
@@ -841,7 +845,15 @@ int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, in
     if (n == 0) return 0;
     CU(ctx, cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> lk(ctx->scratch_mu);
-    int rc = voxel_merge(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream);
+    // voxel_variant: 0 = one-sweep sort when the (key, index) word fits 64 bits, else the pair sort
+    int rc = -4;
+    const int vv = ctx->voxel_variant;
+    if (vv == 3)
+        rc = voxel_merge_sweep<10, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream, ctx->sm_count);
+    else if (vv == 0 || vv == 2)
+        rc = voxel_merge_sweep<8, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream, ctx->sm_count);
+    if (vv == 1 || (vv == 0 && rc == -4))
+        rc = voxel_merge(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream);
     if (rc < 0)
         return fail(ctx, rc == -3 ? PCS_ERR_NOMEM : (rc == -4 ? PCS_ERR_UNSUPPORTED : PCS_ERR_CUDA),
                     "voxel merge failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));

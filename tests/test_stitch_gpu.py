@@ -130,26 +130,70 @@ def test_stitch_errors(ctx):
     assert e.value.status == pcs.PCS_ERR_CAPACITY
 
 
-def test_voxel_merge_vs_oracle(ctx, R):
+@pytest.fixture(scope="module", params=[0, 1, 2, 3], ids=["auto", "pair_sort", "sweep8", "sweep10"])
+def vctx(request):
+    """One context per voxel_variant: auto, the (key, index) pair sort, the one-sweep sort (8 / 10 bit)."""
+    c = pcs.Context(device=0, max_streams=2, voxel_variant=request.param)
+    c.variant = request.param
+    yield c
+    c.close()
+
+
+def test_voxel_merge_vs_oracle(vctx, R):
     rng = np.random.default_rng(11)
-    for n, span, leaf in [(50000, 2000, 10), (200000, 400, 10), (5000, 30000, 25), (4, 10, 10), (1, 5, 1)]:
+    cases = [(50000, 2000, 10), (200000, 400, 10), (5000, 30000, 25), (4, 10, 10), (1, 5, 1), (4096, 300, 10),
+             (4097, 300, 10), (8191, 20, 10), (255, 3, 10), (257, 40000, 10), (70001, 60, 3)]
+    for n, span, leaf in cases:
         rec = random_records(rng, n)
         rec[:, :3] = rng.integers(-span, span, (n, 3))
-        assert np.array_equal(ctx.voxel_merge(rec, leaf), R.voxel_merge(rec, leaf)), (n, span, leaf)
-    assert len(ctx.voxel_merge(np.zeros((0, 5), np.int16), 10)) == 0
+        assert np.array_equal(vctx.voxel_merge(rec, leaf), R.voxel_merge(rec, leaf)), (n, span, leaf)
+    assert len(vctx.voxel_merge(np.zeros((0, 5), np.int16), 10)) == 0
 
 
-def test_voxel_merge_full_size_properties(ctx):
+def test_voxel_merge_skewed_and_unaligned(vctx, R):
+    """Holes pile 1/16 of every camera's points into one voxel (SPEC.md s1): voxels that span many
+    warps, chunks and sort tiles; plus a record pointer that is only 2-byte aligned."""
+    rng = np.random.default_rng(13)
+    n = 300000
+    rec = random_records(rng, n)
+    rec[:, :3] = rng.integers(-3000, 3000, (n, 3))
+    rec[rng.random(n) < 0.6, :3] = (123, -457, 2000)          # one giant voxel
+    rec[rng.random(n) < 0.1, :3] = (-32768, -32768, -32768)    # and one at the corner of the range
+    want = R.voxel_merge(rec, 10)
+    assert np.array_equal(vctx.voxel_merge(rec, 10), want)
+    buf = torch.zeros(n * 5 + 8, dtype=torch.int16, device="cuda")
+    out = torch.zeros(n * 5, dtype=torch.int16, device="cuda")
+    buf[1:1 + n * 5] = torch.from_numpy(rec.reshape(-1)).cuda()
+    cs = torch.cuda.current_stream().cuda_stream
+    nv = vctx.voxel_merge_dev(buf.data_ptr() + 2, n, 10, out.data_ptr(), cs)
+    torch.cuda.synchronize()
+    assert nv == len(want) and np.array_equal(out[: nv * 5].cpu().numpy().reshape(-1, 5), want)
+
+
+def test_voxel_merge_wide_keys_fall_back(vctx, R):
+    """leaf 1 mm: 3 x 16 key bits + 18 index bits do not fit the one-sweep sort word."""
+    rng = np.random.default_rng(14)
+    n = 150000
+    rec = random_records(rng, n)
+    if vctx.variant in (2, 3):
+        with pytest.raises(pcs.PcsError) as e:
+            vctx.voxel_merge(rec, 1)
+        assert e.value.status == pcs.PCS_ERR_UNSUPPORTED
+    else:
+        assert np.array_equal(vctx.voxel_merge(rec, 1), R.voxel_merge(rec, 1))
+
+
+def test_voxel_merge_full_size_properties(vctx):
     # 4 cameras x 1280x720 of plausible geometry: idempotence, sortedness, bounds
     rng = np.random.default_rng(12)
     n = 4 * 921600
     rec = random_records(rng, n)
     rec[:, :3] = (rng.normal(0, 1500, (n, 3))).clip(-32000, 32000).astype(np.int16)
-    m = ctx.voxel_merge(rec, 10)
+    m = vctx.voxel_merge(rec, 10)
     k = np.floor_divide(m[:, :3].astype(np.int64), 10)
     key = (k[:, 2] << 40) + (k[:, 1] << 20) + k[:, 0]
     assert np.all(np.diff(key) > 0)
-    assert np.array_equal(ctx.voxel_merge(m, 10), m)
+    assert np.array_equal(vctx.voxel_merge(m, 10), m)
     assert len(m) == len(np.unique(np.floor_divide(rec[:, :3].astype(np.int32), 10), axis=0))
 
 

@@ -38,6 +38,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cams", type=int, default=16, help="16 x 720p = 147 MB in + 147 MB out: larger than the 126 MB L2")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only-voxel-variant", type=int, default=-1, help="time only this voxel_variant (for ncu runs)")
+    ap.add_argument("--skip-stitch", action="store_true", help="voxel merge only")
     a = ap.parse_args()
     ctx = pcs.Context(device=0, max_streams=a.cams)
     cs = torch.cuda.current_stream().cuda_stream
@@ -60,32 +62,41 @@ def main():
     ptrs, ns = [p.data_ptr() for p in pays], [N * 5] * a.cams
     tfs = [synth.TF_STITCH[c % 8] for c in range(a.cams)]
     res = {"cams": a.cams, "points": total}
-    for d in (1, 2, 4):
-        ms = timed(lambda: ctx.stitch_raw_dev(ptrs, ns, d, st.data_ptr() + 12, total * 10 + 4, cs), a.iters)
-        res["stitch_raw_d%d" % d] = {"ms": ms, "mpoints_s_in": total / ms / 1e3,
-                                     "GBps": (total * 10 / d + total * 10 / d) / ms / 1e6}
-    ms = timed(lambda: ctx.stitch_pcl_dev(ptrs, ns, 1, tfs, st.data_ptr() + 12, total * 10 + 4, None, cs), a.iters)
-    res["stitch_pcl"] = {"ms": ms, "mpoints_s": total / ms / 1e3, "GBps": total * 20 / ms / 1e6}
-    ms = timed(lambda: ctx.stitch_pcl_dev(ptrs, ns, 1, tfs, st.data_ptr() + 12, total * 10 + 4, cloud.data_ptr(), cs), a.iters)
-    res["stitch_pcl_cloud32"] = {"ms": ms, "mpoints_s": total / ms / 1e3, "GBps": total * 52 / ms / 1e6}
+    if not a.skip_stitch:
+        for d in (1, 2, 4):
+            ms = timed(lambda: ctx.stitch_raw_dev(ptrs, ns, d, st.data_ptr() + 12, total * 10 + 4, cs), a.iters)
+            res["stitch_raw_d%d" % d] = {"ms": ms, "mpoints_s_in": total / ms / 1e3,
+                                         "GBps": (total * 10 / d + total * 10 / d) / ms / 1e6}
+        ms = timed(lambda: ctx.stitch_pcl_dev(ptrs, ns, 1, tfs, st.data_ptr() + 12, total * 10 + 4, None, cs), a.iters)
+        res["stitch_pcl"] = {"ms": ms, "mpoints_s": total / ms / 1e3, "GBps": total * 20 / ms / 1e6}
+        ms = timed(lambda: ctx.stitch_pcl_dev(ptrs, ns, 1, tfs, st.data_ptr() + 12, total * 10 + 4, cloud.data_ptr(), cs), a.iters)
+        res["stitch_pcl_cloud32"] = {"ms": ms, "mpoints_s": total / ms / 1e3, "GBps": total * 52 / ms / 1e6}
     # voxel merge of the raw-stitched cloud (records at st+16)
     ctx.stitch_raw_dev(ptrs, ns, 1, st.data_ptr() + 12, total * 10 + 4, cs)
     out = torch.zeros(total * 5, dtype=torch.int16, device="cuda")
     nv = [0]
 
-    def vox():
-        nv[0] = ctx.voxel_merge_dev(st.data_ptr() + 16, total, 10, out.data_ptr(), cs)
-    ms = timed(vox, max(3, a.iters // 4))
-    res["voxel_merge_10mm"] = {"ms": ms, "mpoints_s_in": total / ms / 1e3, "voxels": nv[0]}
-    # K1a: the reference seam itself (vertices + tex coords in), 8 frames of 1280x720 per call
-    nf = 8
-    xyz = torch.randn(nf * N, 3, device="cuda") * 2.0
-    uv = torch.rand(nf * N, 2, device="cuda")
-    col = keep[0][1]
-    pay1 = torch.zeros(nf * N * 5, dtype=torch.int16, device="cuda")
-    ms = timed(lambda: ctx.pack_from_vertices_dev(0, xyz.data_ptr(), uv.data_ptr(), nf * N, col.data_ptr(),
-                                                  pay1.data_ptr(), None, cs), a.iters)
-    res["k1a_from_vertices"] = {"ms": ms, "mpoints_s": nf * N / ms / 1e3, "GBps": nf * N * 30 / ms / 1e6}
+    # voxel_variant: 0 auto (one-sweep sort), 1 (key, index) pair sort, 2 / 3 one-sweep with 8- / 10-bit digits
+    for variant, name in ((0, "voxel_merge_10mm"), (1, "voxel_merge_10mm_pair_sort"), (3, "voxel_merge_10mm_sweep10")):
+        if a.only_voxel_variant >= 0 and variant != a.only_voxel_variant:
+            continue
+        vctx = pcs.Context(device=0, max_streams=1, voxel_variant=variant)
+
+        def vox():
+            nv[0] = vctx.voxel_merge_dev(st.data_ptr() + 16, total, 10, out.data_ptr(), cs)
+        ms = timed(vox, max(3, a.iters // 4))
+        res[name] = {"ms": ms, "mpoints_s_in": total / ms / 1e3, "voxels": nv[0]}
+        vctx.close()
+    if not a.skip_stitch:
+        # K1a: the reference seam itself (vertices + tex coords in), 8 frames of 1280x720 per call
+        nf = 8
+        xyz = torch.randn(nf * N, 3, device="cuda") * 2.0
+        uv = torch.rand(nf * N, 2, device="cuda")
+        col = keep[0][1]
+        pay1 = torch.zeros(nf * N * 5, dtype=torch.int16, device="cuda")
+        ms = timed(lambda: ctx.pack_from_vertices_dev(0, xyz.data_ptr(), uv.data_ptr(), nf * N, col.data_ptr(),
+                                                      pay1.data_ptr(), None, cs), a.iters)
+        res["k1a_from_vertices"] = {"ms": ms, "mpoints_s": nf * N / ms / 1e3, "GBps": nf * N * 30 / ms / 1e6}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "stitch_bench.json"), "w") as f:
         json.dump(res, f, indent=1)
