@@ -47,8 +47,10 @@ def parse():
     ap.add_argument("--variant", type=int, default=0, help="kernel_variant: 0 auto, 1 direct, 2 pipelined")
     ap.add_argument("--tex", default="baseline", choices=["baseline", "aligned"],
                     help="depth->colour extrinsics: 15 mm baseline (D435-like) or identity")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
-                    help="N > 1: fused = K1 stores every tile to all peers (one kernel); nccl = K1 then all-gather")
+    ap.add_argument("--exchange", default="pull", choices=["pull", "fused", "nccl"],
+                    help="N > 1: pull = every rank runs K1 over all cameras, reading the peers' raw frames over NVLink "
+                         "(5 B/pt on the link); fused = K1 stores every tile of records to all peers (10 B/pt); "
+                         "nccl = K1 then all-gather")
     ap.add_argument("--e2e-depth", type=int, default=2, choices=[1, 2], help="frames in flight per camera in the e2e leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -234,7 +236,21 @@ def main():
     slot = S * NPTS * 10
     layout = multigpu.StitchLayout([NPTS] * (world * S), world)
     exchange = "none" if world == 1 else args.exchange
-    sset = None
+    sset = fset = None
+    if exchange == "pull":
+        try:
+            fset = multigpu.SymmetricFrameSet(layout, rank, torch.device("cuda", local), W, H, F)
+            for s in range(S):
+                for f in range(F):
+                    fset.upload(rank * S + s, f, d_np[s, f], c_np[s, f])
+            # every rank computes every camera: one context whose stream ids are the camera indices
+            pctx = pcs.Context(device=local, max_streams=world * S, kernel_variant=args.variant)
+            for cam in range(world * S):
+                pctx.set_stream(cam, pcs.stream_desc(W, H, tf=synth.TF_STITCH[cam % 8], translation=trans))
+        except Exception as e:
+            if rank == 0:
+                print("bench: symmetric memory unavailable (%r); falling back to --exchange nccl" % (e,), file=sys.stderr)
+            exchange, fset = "nccl", None
     if exchange == "fused":
         try:
             sset = multigpu.SymmetricStitchedSet(layout, rank, torch.device("cuda", local), F)
@@ -254,6 +270,8 @@ def main():
     all_jobs = [job(s, f) for f in range(F) for s in range(S)]
     if world == 1:
         batches = [ctx.batch(all_jobs)]
+    elif exchange == "pull":
+        batches = [pctx.batch(fset.pull_jobs(stitched))]
     elif exchange == "fused":
         batches = [ctx.batch_fanout(all_jobs, sset.local_base, sset.nbytes, sset.peer_bases)]
     else:
@@ -264,6 +282,10 @@ def main():
     def step():
         if world == 1:
             batches[0].run(cs.cuda_stream)
+            return
+        if exchange == "pull":
+            batches[0].run(cs.cuda_stream)
+            fset.barrier()       # nobody is still reading this rank's frames
             return
         if exchange == "fused":
             batches[0].run(cs.cuda_stream)
@@ -397,6 +419,7 @@ def main():
         cpu["single_thread_mpoints_s"] = cpu1["value"]
         cpu["single_thread_pack_only_mpoints_s"] = cpu1["pack_only_mpoints_s"]
 
+    link_div = 2 if exchange == "pull" else 1
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps,
@@ -404,9 +427,13 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%d streams/GPU x %d frames x 1280x720 z16 depth + RGB8, fused deproject+transform+"
                                    "colour+pack (K1)%s; depth->colour extrinsics: %s" % (
-                                       S, F, "" if world == 1 else (" + all-gather of the packed records fused into the kernel (peer TMA stores "
-                                                                  "over NVLink)" if exchange == "fused" else
-                                                                  " + in-place NCCL all-gather of the packed records"),
+                                       S, F, "" if world == 1 else {
+                                           "pull": " on every rank over ALL cameras' frames: the peers' raw z16+RGB8 tiles are the "
+                                                   "kernel's own TMA loads from NVLink peer memory (all-gather fused into the "
+                                                   "compute kernel's input pipeline, 5 B/pt on the link)",
+                                           "fused": " + all-gather of the packed records fused into the kernel (peer TMA stores "
+                                                    "over NVLink, 10 B/pt on the link)",
+                                           "nccl": " + in-place NCCL all-gather of the packed records"}[exchange],
                                        "15 mm baseline" if args.tex == "baseline" else "identity"),
                        "streams_per_gpu": S, "frames_per_step": F, "points_per_step": pts_step,
                        "l2": "working set %.0f MB per step per GPU >> 126 MB L2 (no flush needed)" % (
@@ -416,10 +443,11 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "kernel_only": {"ms_per_step": ms_kernel_step, "mpoints_s_per_gpu": S * F * NPTS / (ms_kernel_step * 1e-3) / 1e6},
             "nvlink": None if world == 1 else {
-                "recv_bytes_per_gpu_per_step": (world - 1) * slot * F,
-                "recv_GBps_per_gpu": (world - 1) * slot * F / (ms_step * 1e-3) / 1e9,
-                "note": "every GPU must receive (N-1)/N of the stitched cloud, 10 B/pt: this link rate, not HBM, "
-                        "bounds N > 1 (B200_PROFILING.md: 770 GB/s measured peer copy per direction)"},
+                "recv_bytes_per_gpu_per_step": (world - 1) * slot * F // link_div,
+                "recv_GBps_per_gpu": (world - 1) * slot * F / link_div / (ms_step * 1e-3) / 1e9,
+                "note": "every GPU must take in (N-1)/N of the stitched cloud -- as 10 B/pt records (fused, nccl) or as "
+                        "5 B/pt raw frames it deprojects itself (pull): this link rate, not HBM, bounds N > 1 "
+                        "(B200_PROFILING.md: 770 GB/s measured peer copy per direction)"},
         }
         print(json.dumps(line))
     if world > 1:

@@ -136,3 +136,79 @@ class SymmetricStitchedSet:
     def barrier(self):
         """Device-side barrier on the current stream: all ranks' fused launches have finished."""
         self.handle.barrier()
+
+
+def frame_slots(width, height, stride, cams_per_rank_max, n_frames):
+    """Byte offsets inside one rank's raw-frame allocation (the same on every rank):
+    ``depth_off(local_cam, frame)``, ``color_off(local_cam, frame)`` and the total size.  Every frame is
+    256-byte aligned (the pipelined kernel needs 16)."""
+    dz = (width * height * 2 + 255) & ~255
+    dc = (height * stride + 255) & ~255
+    per_frame = dz + dc
+    total = max(1, cams_per_rank_max) * n_frames * per_frame
+
+    def depth_off(local_cam, frame):
+        return (local_cam * n_frames + frame) * per_frame
+
+    def color_off(local_cam, frame):
+        return depth_off(local_cam, frame) + dz
+
+    return depth_off, color_off, total
+
+
+class SymmetricFrameSet:
+    """The raw z16 depth + RGB8 colour frames of this rank's cameras, in symmetric memory, so that a
+    peer's K1 can read them over NVLink.
+
+    This is the *pull* exchange: instead of all-gathering the 10-byte records K1 produced, every
+    rank runs K1 over ALL cameras -- its own from HBM, the peers' through TMA bulk loads from peer
+    memory -- and writes the complete stitched buffer locally.  5 B/pt cross the link instead of
+    10 B/pt, the transfer is the kernel's own input pipeline (all-gather fused into the compute
+    kernel, tile by tile), and no rank ever writes to another rank's memory.  K1 is ~5x faster
+    than the link, so recomputing a peer's records is cheaper than receiving them.
+    """
+
+    def __init__(self, layout: StitchLayout, rank: int, device, width, height, n_frames, stride=None, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.layout, self.rank, self.n_frames = layout, rank, n_frames
+        self.width, self.height = width, height
+        self.stride = stride if stride is not None else width * 3
+        cmax = max(len(c) for c in layout.cams_of)
+        self.depth_off, self.color_off, self.nbytes = frame_slots(width, height, self.stride, cmax, n_frames)
+        self.raw = symm.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.raw.zero_()
+        self.handle = symm.rendezvous(self.raw, group if group is not None else dist.group.WORLD)
+        self.bases = list(self.handle.buffer_ptrs)
+        assert self.bases[rank] == self.raw.data_ptr()
+
+    def upload(self, cam, frame, z16: np.ndarray, color: np.ndarray):
+        """Place one of this rank's frames (host arrays) in its slot."""
+        lc = self.layout.cams_of[self.rank].index(cam)
+        dz = torch.from_numpy(np.ascontiguousarray(z16).view(np.uint8).reshape(-1))
+        dc = torch.from_numpy(np.ascontiguousarray(color).reshape(-1))
+        o = self.depth_off(lc, frame)
+        self.raw[o:o + dz.numel()].copy_(dz)
+        o = self.color_off(lc, frame)
+        self.raw[o:o + dc.numel()].copy_(dc)
+
+    def ptrs(self, cam, frame):
+        """(z16_ptr, colour_ptr) of any camera's frame as seen from this rank: local HBM for its own
+        cameras, NVLink peer memory otherwise."""
+        owner = self.layout.rank_of(cam)
+        lc = self.layout.cams_of[owner].index(cam)
+        base = self.bases[owner]
+        return base + self.depth_off(lc, frame), base + self.color_off(lc, frame)
+
+    def pull_jobs(self, stitched_frames):
+        """K1 jobs for EVERY camera and frame: (stream = camera index, z16, colour, local stitched slot)."""
+        n_cams = len(self.layout.points)
+        jobs = []
+        for f in range(self.n_frames):
+            for cam in range(n_cams):
+                z, c = self.ptrs(cam, f)
+                jobs.append((cam, z, c, stitched_frames[f].slot_ptr(cam)))
+        return jobs
+
+    def barrier(self):
+        """All ranks have finished reading each other's frames (call before overwriting them)."""
+        self.handle.barrier()

@@ -28,6 +28,34 @@ def test_partition_and_layout():
         multigpu.StitchLayout([921600] * 300, 8)      # > int32 header
 
 
+def test_pull_exchange_job_table():
+    """The pull exchange's host logic: frame slots do not overlap, and every rank's job table names
+    every camera once per frame, reading the owner's allocation and writing the local stitched slot."""
+    W, H, F = 64, 8, 3
+    L = multigpu.StitchLayout([W * H] * 5, 2)                  # ranks own cams [0,1,2] and [3,4]
+    depth_off, color_off, total = multigpu.frame_slots(W, H, W * 3, 3, F)
+    spans = []
+    for lc in range(3):
+        for f in range(F):
+            spans += [(depth_off(lc, f), W * H * 2), (color_off(lc, f), H * W * 3)]
+    spans.sort()
+    assert all(o % 256 == 0 for o, _ in spans)
+    assert all(a + n <= b for (a, n), (b, _) in zip(spans, spans[1:])) and spans[-1][0] + spans[-1][1] <= total
+    for rank in range(2):
+        fs = multigpu.SymmetricFrameSet.__new__(multigpu.SymmetricFrameSet)
+        fs.layout, fs.rank, fs.n_frames = L, rank, F
+        fs.depth_off, fs.color_off, fs.nbytes = depth_off, color_off, total
+        fs.bases = [0x10000000, 0x20000000]
+        stitched = [multigpu.StitchedBuffer(L, rank, "cpu") for _ in range(F)]
+        jobs = fs.pull_jobs(stitched)
+        assert [j[0] for j in jobs] == list(range(5)) * F
+        for k, (cam, z, c, out) in enumerate(jobs):
+            f, owner = k // 5, L.rank_of(cam)
+            lc = L.cams_of[owner].index(cam)
+            assert z == fs.bases[owner] + depth_off(lc, f) and c == fs.bases[owner] + color_off(lc, f)
+            assert out == stitched[f].slot_ptr(cam)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

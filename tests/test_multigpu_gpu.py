@@ -1,6 +1,7 @@
-"""-m gpu, needs >= 2 GPUs (gpurun --gpus 2): one process per GPU over NCCL.  Both exchange paths
--- the fused K1 + peer-store kernel (pcs_b200_batch_create_fanout) and the NCCL all-gather
-baseline -- must leave the reference's stitched layout, bit-exact against the oracle, on every rank."""
+"""-m gpu, needs >= 2 GPUs (gpurun --gpus 2): one process per GPU over NCCL.  All exchange paths
+-- K1 pulling the peers' raw frames over NVLink (SymmetricFrameSet), the fused K1 + peer-store
+kernel (pcs_b200_batch_create_fanout) and the NCCL all-gather baseline -- must leave the
+reference's stitched layout, bit-exact against the oracle, on every rank."""
 import os
 import socket
 
@@ -62,7 +63,23 @@ def _worker(rank, world, port, cams_total, out_dir):
     for f in range(n_frames):
         plain[f].gather()
     torch.cuda.synchronize()
+    # pull: every rank computes every camera, the peers' frames come through NVLink peer memory
+    fset = multigpu.SymmetricFrameSet(layout, rank, dev, W, H, n_frames)
+    pulled = [multigpu.StitchedBuffer(layout, rank, dev) for _ in range(n_frames)]
+    for cam in range(cams_total):
+        ctx.set_stream(cam, pcs.stream_desc(W, H, tf=synth.TF_STITCH[cam % 8], translation=synth.D2C_BASELINE))
+    for cam in layout.cams_of[rank]:
+        for f in range(n_frames):
+            fset.upload(cam, f, synth.depth_frame(W, H, cam, f), synth.color_frame(W, H, cam, f))
+    torch.cuda.synchronize()
+    fset.barrier()
+    bq = ctx.batch(fset.pull_jobs(pulled))
+    assert bq.launches == 1
+    bq.run(cs)
+    fset.barrier()
+    torch.cuda.synchronize()
     for f in range(n_frames):
+        np.save(os.path.join(out_dir, "pull_r%d_f%d.npy" % (rank, f)), pulled[f].wire_bytes().cpu().numpy())
         np.save(os.path.join(out_dir, "fused_r%d_f%d.npy" % (rank, f)), sset.frames[f].wire_bytes().cpu().numpy())
         np.save(os.path.join(out_dir, "nccl_r%d_f%d.npy" % (rank, f)), plain[f].wire_bytes().cpu().numpy())
     dist.barrier()
@@ -70,7 +87,7 @@ def _worker(rank, world, port, cams_total, out_dir):
 
 
 @pytest.mark.parametrize("cams_total", [4, 5], ids=["equal", "ragged"])
-def test_fused_and_nccl_exchange_match_oracle(tmp_path, cams_total):
+def test_pull_fused_and_nccl_exchange_match_oracle(tmp_path, cams_total):
     import oracle
     from pointcloud_stitching_b200 import synth
     world = 2
@@ -81,6 +98,6 @@ def test_fused_and_nccl_exchange_match_oracle(tmp_path, cams_total):
         want = R.concat([R.frame(cal, synth.depth_frame(W, H, cam, f), synth.color_frame(W, H, cam, f), 3, W * 3,
                                  synth.TF_STITCH[cam % 8]) for cam in range(cams_total)], 1)
         for r in range(world):
-            for kind in ("fused", "nccl"):
+            for kind in ("pull", "fused", "nccl"):
                 got = np.load(os.path.join(str(tmp_path), "%s_r%d_f%d.npy" % (kind, r, f)))
                 assert np.array_equal(got, want), (kind, r, f)
