@@ -200,13 +200,26 @@ PCS_API int pcs_b200_stitch_pcl(pcs_ctx *ctx, const int16_t *const *payload_host
 
 /* Voxel-grid merge of n records (own integer specification, oracle/SPEC.md s3; the
  * reference includes pcl/filters/voxel_grid.h but never calls it).  Returns the
- * number of voxels written to out_dev (capacity n records).  n * max(255, leaf_mm - 1)
- * must stay below 2^32 (uint32 sums: n <= 16.8 M points at the 10 mm leaf).  The call
+ * number of voxels written to out_dev (capacity n records).  n * max(256, leaf_mm)
+ * must stay below 2^32 (uint32 sums: n < 16.8 M points at the 10 mm leaf).  The call
  * synchronises cuda_stream once (the voxel count has to reach the host). */
 PCS_API int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
                              int16_t *out_dev, void *cuda_stream);
 PCS_API int pcs_b200_voxel_merge(pcs_ctx *ctx, const int16_t *records_host, int n, int leaf_mm,
                          int16_t *out_host);
+
+/* Sharded voxel merge (multi-GPU: SURVEY s8(e) "sharded by voxel-key range").  The grid is cut
+ * along z into n_slabs slabs of nearly equal population: slab r holds the points with
+ * kz_splits[r] <= floor(z / leaf_mm) < kz_splits[r + 1] (kz_splits: n_slabs + 1 host ints;
+ * slab_points: n_slabs host ints or NULL).  The plan depends only on the records, so ranks that hold
+ * the same stitched cloud compute the same cuts without communicating.
+ * pcs_b200_voxel_merge_slab_dev merges one slab; because voxels are emitted in ascending
+ * (kz, ky, kx) order, the outputs of slabs 0 .. n_slabs-1 concatenated are exactly what
+ * pcs_b200_voxel_merge_dev returns for the whole cloud.  Returns the slab's voxel count. */
+PCS_API int pcs_b200_voxel_slab_plan_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
+                                 int n_slabs, int32_t *kz_splits, int32_t *slab_points, void *cuda_stream);
+PCS_API int pcs_b200_voxel_merge_slab_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
+                                  int kz_lo, int kz_hi, int16_t *out_dev, void *cuda_stream);
 
 /* Blocks until everything issued on cuda_stream by this context has finished. */
 PCS_API int pcs_b200_synchronize(pcs_ctx *ctx, void *cuda_stream);

@@ -127,6 +127,8 @@ def _load():
         "pcs_b200_stitch_pcl": (C.c_int, [vp, C.POINTER(vp), i32p, C.c_int, C.c_int, vp, vp, C.c_size_t]),
         "pcs_b200_voxel_merge_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
         "pcs_b200_voxel_merge": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
+        "pcs_b200_voxel_slab_plan_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, i32p, i32p, vp]),
+        "pcs_b200_voxel_merge_slab_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         "pcs_b200_synchronize": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -318,6 +320,17 @@ class Context:
     def voxel_merge_dev(self, records_ptr, n, leaf_mm, out_ptr, cuda_stream=0):
         return self._check(lib.pcs_b200_voxel_merge_dev(self.handle, records_ptr, n, leaf_mm, out_ptr,
                                                         cuda_stream))
+
+    def voxel_slab_plan_dev(self, records_ptr, n, leaf_mm, n_slabs, cuda_stream=0):
+        """(kz_splits[n_slabs + 1], slab_points[n_slabs]): equal-population cuts of the grid along z."""
+        splits, pts = (C.c_int32 * (n_slabs + 1))(), (C.c_int32 * n_slabs)()
+        self._check(lib.pcs_b200_voxel_slab_plan_dev(self.handle, records_ptr, n, leaf_mm, n_slabs, splits, pts,
+                                                     cuda_stream))
+        return list(splits), list(pts)
+
+    def voxel_merge_slab_dev(self, records_ptr, n, leaf_mm, kz_lo, kz_hi, out_ptr, cuda_stream=0):
+        return self._check(lib.pcs_b200_voxel_merge_slab_dev(self.handle, records_ptr, n, leaf_mm, kz_lo, kz_hi,
+                                                             out_ptr, cuda_stream))
 
     def synchronize(self, cuda_stream=0):
         self._check(lib.pcs_b200_synchronize(self.handle, cuda_stream))

@@ -834,19 +834,31 @@ int pcs_b200_stitch_pcl(pcs_ctx *ctx, const int16_t *const *payload_host, const 
 }
 
 // ---- voxel merge -----------------------------------------------------------------
+static int voxel_args_ok(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, const void *out) {
+    if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
+    if (n < 0 || leaf_mm < 1 || leaf_mm > 32767 || (n && (!records_dev || !out)))
+        return fail(ctx, PCS_ERR_INVALID, "bad voxel-merge arguments");
+    // the per-voxel sums are uint32 (oracle/SPEC.md s3): 255 * n and (leaf - 1) * n must fit, with
+    // room for one more count (the mean's +-1 fix-up works modulo 2^32)
+    if ((long long)n * 256 > 0xFFFFFFFFll || (long long)n * leaf_mm > 0xFFFFFFFFll)
+        return fail(ctx, PCS_ERR_UNSUPPORTED, "voxel merge: n * max(256, leaf_mm) must stay below 2^32");
+    return PCS_OK;
+}
+
+static int voxel_fail(pcs_ctx *ctx, int rc) {
+    return fail(ctx, rc == -3 ? PCS_ERR_NOMEM : (rc == -4 ? PCS_ERR_UNSUPPORTED : PCS_ERR_CUDA),
+                "voxel merge failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+}
+
 int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
                              int16_t *out_dev, void *cuda_stream) {
-    if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
-    if (n < 0 || leaf_mm < 1 || leaf_mm > 32767 || (n && (!records_dev || !out_dev)))
-        return fail(ctx, PCS_ERR_INVALID, "bad voxel-merge arguments");
-    // the per-voxel sums are uint32 (oracle/SPEC.md s3): 255 * n and (leaf - 1) * n must fit
-    if ((long long)n * 255 > 0xFFFFFFFFll || (long long)n * (leaf_mm - 1) > 0xFFFFFFFFll)
-        return fail(ctx, PCS_ERR_UNSUPPORTED, "voxel merge: n * max(255, leaf_mm - 1) must stay below 2^32");
+    int rc = voxel_args_ok(ctx, records_dev, n, leaf_mm, out_dev);
+    if (rc) return rc;
     if (n == 0) return 0;
     CU(ctx, cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> lk(ctx->scratch_mu);
     // voxel_variant: 0 = one-sweep sort when the (key, index) word fits 64 bits, else the pair sort
-    int rc = -4;
+    rc = -4;
     const int vv = ctx->voxel_variant;
     if (vv == 3)
         rc = voxel_merge_sweep<10, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream, ctx->sm_count);
@@ -854,10 +866,35 @@ int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, in
         rc = voxel_merge_sweep<8, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream, ctx->sm_count);
     if (vv == 1 || (vv == 0 && rc == -4))
         rc = voxel_merge(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream);
-    if (rc < 0)
-        return fail(ctx, rc == -3 ? PCS_ERR_NOMEM : (rc == -4 ? PCS_ERR_UNSUPPORTED : PCS_ERR_CUDA),
-                    "voxel merge failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
-    return rc;
+    return rc < 0 ? voxel_fail(ctx, rc) : rc;
+}
+
+int pcs_b200_voxel_slab_plan_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, int n_slabs,
+                                 int32_t *kz_splits, int32_t *slab_points, void *cuda_stream) {
+    int rc = voxel_args_ok(ctx, records_dev, n, leaf_mm, kz_splits);
+    if (rc) return rc;
+    if (n_slabs < 1 || n_slabs > 1024 || !kz_splits) return fail(ctx, PCS_ERR_INVALID, "1 <= n_slabs <= 1024");
+    CU(ctx, cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->scratch_mu);
+    rc = voxel_slab_plan(ctx->voxel, records_dev, n, leaf_mm, n_slabs, kz_splits, slab_points,
+                         (cudaStream_t)cuda_stream, ctx->sm_count);
+    return rc < 0 ? voxel_fail(ctx, rc) : PCS_OK;
+}
+
+int pcs_b200_voxel_merge_slab_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, int kz_lo,
+                                  int kz_hi, int16_t *out_dev, void *cuda_stream) {
+    int rc = voxel_args_ok(ctx, records_dev, n, leaf_mm, out_dev);
+    if (rc) return rc;
+    if (n == 0 || kz_lo >= kz_hi) return 0;
+    CU(ctx, cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->scratch_mu);
+    if (ctx->voxel_variant == 3)
+        rc = voxel_merge_sweep<10, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream,
+                                            ctx->sm_count, true, kz_lo, kz_hi);
+    else
+        rc = voxel_merge_sweep<8, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream,
+                                           ctx->sm_count, true, kz_lo, kz_hi);
+    return rc < 0 ? voxel_fail(ctx, rc) : rc;
 }
 
 int pcs_b200_voxel_merge(pcs_ctx *ctx, const int16_t *records_host, int n, int leaf_mm,

@@ -19,6 +19,8 @@
 // of the additions.  Needs 3*bits + ceil(log2 n) <= 64 and 24 + 3*ceil(log2 leaf) <= 64; the caller
 // falls back to the (key, idx) pair sort of pcs_voxel.cuh otherwise.
 #pragma once
+#include <vector>
+
 #include "pcs_voxel.cuh"
 
 namespace pcs {
@@ -26,13 +28,31 @@ namespace pcs {
 constexpr uint32_t SW_AGG = 1u << 30, SW_PREFIX = 2u << 30, SW_VALUE = (1u << 30) - 1;
 constexpr int SW_SPIN_LIMIT = 1 << 20;      // ~0.5 s of polling: a lost predecessor becomes an error, not a hang
 constexpr int SW_KH_THREADS = 256, SW_KH_ITEMS = 8, SW_KH_TILE = SW_KH_THREADS * SW_KH_ITEMS;
+constexpr int SW_GROUP = 16;                // tiles per look-back group (= one look-back window)
 constexpr int SW_CHUNK_ROUNDS = 8, SW_CHUNK = 32 * SW_CHUNK_ROUNDS;    // points per warp in the reduce
 
+// Key geometry.  With K = ceil(32768 / leaf) every coordinate v becomes u = v + leaf*K >= 0 and
+// q = floor(u / leaf) = floor(v / leaf) + K  (one multiply-high: u < 2^17, magic = floor(2^40 / leaf) + 1
+// is exact for u * leaf < 2^40).  A first pass over the records finds the occupied box
+// [x0, x1] x [y0, y1] x [z0, z1] in q units -- what PCL's VoxelGrid does with getMinMax3D before it
+// builds its indices -- so the sort key only spends the bits the scene needs:
+//     key = ((qz - z0) * dy + (qy - y0)) * dx + (qx - x0)        dx, dy = box extents (mixed radix)
+// A z-slab filter [z_lo, z_hi) (q units) restricts the merge to a horizontal slice of the grid: the
+// slices of disjoint slabs, concatenated in slab order, are the full result (multi-GPU sharding).
 struct SweepGeom {
-    int leaf, kmin, bits;   // key field = floor(v / leaf) - kmin, `bits` wide (as VoxelGeom)
-    int idx_bits;           // low bits of the sort word hold the point index
-    int off_bits;           // width of one in-voxel offset (0 .. leaf-1) in the gather word
+    int leaf, K, bias;            // bias = leaf * K
+    unsigned long long magic;     // floor(2^40 / leaf) + 1
+    int x0, y0, z0;               // box origin, q units
+    unsigned dx, dy;              // box extents along x and y (the key is mixed radix)
+    unsigned long long mdx, mdy;  // floor(2^64 / d) + 1 for d = dx, dy (0 when d == 1): key / d = umul64hi(key, m)
+    int idx_bits;                 // low bits of the sort word hold the point's slot
+    int off_bits;                 // width of one in-voxel offset (0 .. leaf-1) in the gather word
+    int z_lo, z_hi;               // keep qz in [z_lo, z_hi)
 };
+
+__device__ __forceinline__ uint32_t sw_q(int v, const SweepGeom &g) {
+    return (uint32_t)(((unsigned long long)(uint32_t)(v + g.bias) * g.magic) >> 40);
+}
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
@@ -45,55 +65,169 @@ __device__ __forceinline__ void st_volatile_v4(uint32_t *p, uint4 v) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// eight consecutive records (40 halfwords) as 20 words; past-the-end halfwords read as 0
+__device__ __forceinline__ void sw_load8(const int16_t *__restrict__ rec, int n, int first, bool fast, uint32_t (&w)[20]) {
+    if (fast) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(rec + 5 * (size_t)first);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const uint4 q = __ldg(p + j);
+            w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w;
+        }
+    } else {
+        const size_t lim = 5 * (size_t)n, at = 5 * (size_t)first;
+#pragma unroll
+        for (int j = 0; j < 20; ++j) {
+            const uint32_t lo = at + 2 * j < lim ? (uint16_t)rec[at + 2 * j] : 0u;
+            const uint32_t hi = at + 2 * j + 1 < lim ? (uint16_t)rec[at + 2 * j + 1] : 0u;
+            w[j] = lo | (hi << 16);
+        }
+    }
+}
+__device__ __forceinline__ int sw_half(const uint32_t (&w)[20], int h) {   // halfword h, sign-extended
+    return (int16_t)(w[h >> 1] >> (16 * (h & 1)));
+}
+
+// ---- 0. occupied box, slab population, optional histogram over qz ---------------------------
+// bounds[0..2] = min qx, qy, qz; bounds[3..5] = max; bounds[6] = points inside the slab.
+// zhist (HIST): points per qz plane over ALL points (the plan for cutting slabs).
+template <bool HIST>
+__global__ void __launch_bounds__(SW_KH_THREADS)
+sw_bounds(const int16_t *__restrict__ rec, int n, SweepGeom g, uint32_t *__restrict__ bounds,
+          uint32_t *__restrict__ zhist, int zbins, int zhist_in_smem) {
+    extern __shared__ uint32_t sw_zh[];
+    __shared__ uint32_t red[7];
+    if (threadIdx.x < 7) red[threadIdx.x] = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
+    uint32_t *zh = (HIST && zhist_in_smem) ? sw_zh : zhist;
+    if (HIST && zhist_in_smem)
+        for (int k = threadIdx.x; k < zbins; k += SW_KH_THREADS) sw_zh[k] = 0;
+    __syncthreads();
+    const bool aligned = (((uintptr_t)rec) & 15) == 0;
+    const int n_tiles = (n + SW_KH_TILE - 1) / SW_KH_TILE;
+    uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0, 0, 0}, inside = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int first = tile * SW_KH_TILE + threadIdx.x * SW_KH_ITEMS;
+        const int cnt = max(0, min(SW_KH_ITEMS, n - first));
+        if (cnt == 0) continue;
+        uint32_t w[20];
+        sw_load8(rec, n, first, cnt == SW_KH_ITEMS && aligned, w);
+        uint32_t prev = 0, run = 0;
+#pragma unroll
+        for (int k = 0; k < SW_KH_ITEMS; ++k) {
+            if (k < cnt) {
+                const uint32_t qx = sw_q(sw_half(w, 5 * k), g), qy = sw_q(sw_half(w, 5 * k + 1), g),
+                               qz = sw_q(sw_half(w, 5 * k + 2), g);
+                if ((int)qz >= g.z_lo && (int)qz < g.z_hi) {
+                    mn[0] = min(mn[0], qx); mn[1] = min(mn[1], qy); mn[2] = min(mn[2], qz);
+                    mx[0] = max(mx[0], qx); mx[1] = max(mx[1], qy); mx[2] = max(mx[2], qz);
+                    ++inside;
+                }
+                if (HIST) {
+                    if (run && qz == prev) {
+                        ++run;
+                    } else {
+                        if (run) atomicAdd(zh + prev, run);
+                        prev = qz;
+                        run = 1;
+                    }
+                }
+            }
+        }
+        if (HIST && run) atomicAdd(zh + prev, run);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = __reduce_min_sync(0xffffffffu, mn[a]);
+        mx[a] = __reduce_max_sync(0xffffffffu, mx[a]);
+    }
+    inside = __reduce_add_sync(0xffffffffu, inside);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(red + a, mn[a]);
+            atomicMax(red + 3 + a, mx[a]);
+        }
+        atomicAdd(red + 6, inside);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicMin(bounds + threadIdx.x, red[threadIdx.x]);
+    else if (threadIdx.x < 6) atomicMax(bounds + threadIdx.x, red[threadIdx.x]);
+    else if (threadIdx.x == 6 && red[6]) atomicAdd(bounds + 6, red[6]);
+    if (HIST && zhist_in_smem)
+        for (int k = threadIdx.x; k < zbins; k += SW_KH_THREADS) {
+            const uint32_t v = sw_zh[k];
+            if (v) atomicAdd(zhist + k, v);
+        }
+}
+
 // ---- 1. sort words, gather words and all digit histograms -------------------------------
-// pay[i] = R | G<<8 | B<<16 | (x - leaf*kx) << 24 | (y - leaf*ky) << (24+ob) | (z - leaf*kz) << (24+2ob):
-// everything the reduce needs from a record in one aligned 8-byte load.
-template <int BITS>
+// pay[slot] = R | G<<8 | B<<16 | (x - leaf*kx) << 24 | (y - leaf*ky) << (24+ob) | (z - leaf*kz) << (24+2ob):
+// everything the reduce needs from a record in one aligned 8-byte load.  Without a slab filter a
+// point's slot is its index; with one, the tile's survivors take consecutive slots reserved with one
+// atomicAdd per tile (their order is irrelevant: the slot only ties the sort word to its gather word,
+// and the per-voxel sums are integers).
+template <int BITS, bool FILTER>
 __global__ void __launch_bounds__(SW_KH_THREADS)
 sw_keys_hist(const int16_t *__restrict__ rec, int n, SweepGeom g, int passes,
-             uint64_t *__restrict__ words, uint64_t *__restrict__ pay, uint32_t *__restrict__ ghist) {
+             uint64_t *__restrict__ words, uint64_t *__restrict__ pay, uint32_t *__restrict__ ghist,
+             uint32_t *__restrict__ slot_counter) {
     constexpr int BINS = 1 << BITS;
     extern __shared__ uint32_t sw_hist[];    // [passes][BINS]
+    __shared__ uint32_t warp_cnt[SW_KH_THREADS / 32], s_base;
     for (int k = threadIdx.x; k < passes * BINS; k += SW_KH_THREADS) sw_hist[k] = 0;
     __syncthreads();
     const bool aligned = (((uintptr_t)rec) & 15) == 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_tiles = (n + SW_KH_TILE - 1) / SW_KH_TILE;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int first = tile * SW_KH_TILE + threadIdx.x * SW_KH_ITEMS;
         const int cnt = max(0, min(SW_KH_ITEMS, n - first));
-        uint32_t w[20];     // 8 records = 40 halfwords
-        if (cnt == SW_KH_ITEMS && aligned) {
-            const uint4 *p = reinterpret_cast<const uint4 *>(rec + 5 * (size_t)first);
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const uint4 q = __ldg(p + j);
-                w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w;
-            }
-        } else {
-            const size_t lim = 5 * (size_t)n, at = 5 * (size_t)first;
-#pragma unroll
-            for (int j = 0; j < 20; ++j) {
-                const uint32_t lo = at + 2 * j < lim ? (uint16_t)rec[at + 2 * j] : 0u;
-                const uint32_t hi = at + 2 * j + 1 < lim ? (uint16_t)rec[at + 2 * j + 1] : 0u;
-                w[j] = lo | (hi << 16);
-            }
-        }
+        uint32_t w[20];
+        if (cnt > 0) sw_load8(rec, n, first, cnt == SW_KH_ITEMS && aligned, w);
         uint64_t word[SW_KH_ITEMS], pw[SW_KH_ITEMS];
+        uint32_t keep = 0;     // bit k: item k exists and lies inside the slab
 #pragma unroll
         for (int k = 0; k < SW_KH_ITEMS; ++k) {
-            const int h = 5 * k;
-            const int x = (int16_t)(w[h >> 1] >> (16 * (h & 1)));
-            const int y = (int16_t)(w[(h + 1) >> 1] >> (16 * ((h + 1) & 1)));
-            const int z = (int16_t)(w[(h + 2) >> 1] >> (16 * ((h + 2) & 1)));
-            const uint32_t s3 = (w[(h + 3) >> 1] >> (16 * ((h + 3) & 1))) & 0xFFFFu;
-            const uint32_t s4 = (w[(h + 4) >> 1] >> (16 * ((h + 4) & 1))) & 0xFFu;
-            const int fx = floordiv_i(x, g.leaf), fy = floordiv_i(y, g.leaf), fz = floordiv_i(z, g.leaf);
-            const uint64_t kx = (uint64_t)(fx - g.kmin), ky = (uint64_t)(fy - g.kmin), kz = (uint64_t)(fz - g.kmin);
-            word[k] = (((kz << (2 * g.bits)) | (ky << g.bits) | kx) << g.idx_bits) | (uint64_t)(uint32_t)(first + k);
-            const uint64_t ox = (uint64_t)(x - g.leaf * fx), oy = (uint64_t)(y - g.leaf * fy), oz = (uint64_t)(z - g.leaf * fz);
-            pw[k] = (uint64_t)(s3 | (s4 << 16)) | (ox << 24) | (oy << (24 + g.off_bits)) | (oz << (24 + 2 * g.off_bits));
+            if (k < cnt) {
+                const int x = sw_half(w, 5 * k), y = sw_half(w, 5 * k + 1), z = sw_half(w, 5 * k + 2);
+                const uint32_t s3 = (uint32_t)sw_half(w, 5 * k + 3) & 0xFFFFu, s4 = (uint32_t)sw_half(w, 5 * k + 4) & 0xFFu;
+                const uint32_t qx = sw_q(x, g), qy = sw_q(y, g), qz = sw_q(z, g);
+                if (!FILTER || ((int)qz >= g.z_lo && (int)qz < g.z_hi)) keep |= 1u << k;
+                word[k] = ((uint64_t)(qz - (uint32_t)g.z0) * g.dy + (uint64_t)(qy - (uint32_t)g.y0)) * g.dx +
+                          (uint64_t)(qx - (uint32_t)g.x0);
+                const uint64_t ox = (uint64_t)(uint32_t)(x + g.bias - g.leaf * (int)qx),
+                               oy = (uint64_t)(uint32_t)(y + g.bias - g.leaf * (int)qy),
+                               oz = (uint64_t)(uint32_t)(z + g.bias - g.leaf * (int)qz);
+                pw[k] = (uint64_t)(s3 | (s4 << 16)) | (ox << 24) | (oy << (24 + g.off_bits)) | (oz << (24 + 2 * g.off_bits));
+            } else {
+                word[k] = 0; pw[k] = 0;
+            }
         }
-        if (cnt == SW_KH_ITEMS) {
+        uint32_t slot0 = (uint32_t)first;     // slot of this thread's first surviving item
+        if (FILTER) {
+            const uint32_t c = __popc(keep);
+            uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            if (lane == 31) warp_cnt[warp] = inc;
+            __syncthreads();
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int v = 0; v < SW_KH_THREADS / 32; ++v) {
+                const uint32_t t = warp_cnt[v];
+                if (v < warp) before += t;
+                total += t;
+            }
+            if (threadIdx.x == 0) s_base = total ? atomicAdd(slot_counter, total) : 0u;
+            __syncthreads();
+            slot0 = s_base + before + inc - c;
+        }
+        if (!FILTER && cnt == SW_KH_ITEMS) {
+#pragma unroll
+            for (int k = 0; k < SW_KH_ITEMS; ++k) word[k] = (word[k] << g.idx_bits) | (uint64_t)(slot0 + k);
             uint4 *o = reinterpret_cast<uint4 *>(words + first), *q = reinterpret_cast<uint4 *>(pay + first);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -103,9 +237,15 @@ sw_keys_hist(const int16_t *__restrict__ rec, int n, SweepGeom g, int passes,
                                   (uint32_t)pw[2 * j + 1], (uint32_t)(pw[2 * j + 1] >> 32));
             }
         } else {
+            uint32_t slot = slot0;
 #pragma unroll
             for (int k = 0; k < SW_KH_ITEMS; ++k)
-                if (k < cnt) { words[first + k] = word[k]; pay[first + k] = pw[k]; }
+                if ((keep >> k) & 1u) {
+                    word[k] = (word[k] << g.idx_bits) | (uint64_t)slot;
+                    words[slot] = word[k];
+                    pay[slot] = pw[k];
+                    ++slot;
+                }
         }
         // Neighbouring pixels mostly share their upper digits: count runs, not elements, and let the
         // lanes whose last run has the same digit add it once (a same-address shared-memory atomic
@@ -113,25 +253,39 @@ sw_keys_hist(const int16_t *__restrict__ rec, int n, SweepGeom g, int passes,
         for (int p = 0; p < passes; ++p) {
             const int shift = g.idx_bits + p * BITS;
             uint32_t *h = sw_hist + p * BINS;
-            uint32_t prev = cnt > 0 ? ((uint32_t)(word[0] >> shift) & (BINS - 1)) : (uint32_t)(BINS + (threadIdx.x & 31));
-            uint32_t run = cnt > 0 ? 1u : 0u;
+            uint32_t prev = (uint32_t)(BINS + lane), run = 0;
 #pragma unroll
-            for (int k = 1; k < SW_KH_ITEMS; ++k) {
-                if (k < cnt) {
+            for (int k = 0; k < SW_KH_ITEMS; ++k) {
+                if ((keep >> k) & 1u) {
                     const uint32_t d = (uint32_t)(word[k] >> shift) & (BINS - 1);
-                    if (d == prev) {
+                    if (run && d == prev) {
                         ++run;
                     } else {
-                        atomicAdd(h + prev, run);
+                        if (run) atomicAdd(h + prev, run);
                         prev = d;
                         run = 1;
                     }
                 }
             }
-            const uint32_t peers = __match_any_sync(0xffffffffu, prev);
-            const uint32_t tot = __reduce_add_sync(peers, run);
-            if (cnt > 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(h + prev, tot);
+            // merge the lanes' last runs: consecutive lanes with the same digit add once (a masked
+            // __reduce_add_sync over match_any groups compiles to a loop over the groups -- 15 trips
+            // per call on this data -- so the merge is a plain inclusive scan + head flags instead)
+            const uint32_t up = __shfl_up_sync(0xffffffffu, prev, 1);
+            const bool head = lane == 0 || up != prev;
+            uint32_t inc = run;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            const uint32_t hm = __ballot_sync(0xffffffffu, head);
+            const uint32_t above = lane == 31 ? 0u : (hm & (0xFFFFFFFEu << lane));     // heads after this lane
+            const int last = above ? __ffs(above) - 2 : 31;                             // last lane of my segment
+            const uint32_t seg_end = __shfl_sync(0xffffffffu, inc, last);
+            const uint32_t tot = seg_end - (inc - run);
+            if (head && tot) atomicAdd(h + prev, tot);
         }
+        if (FILTER) __syncthreads();   // warp_cnt / s_base are rewritten by the next tile
     }
     __syncthreads();
     for (int k = threadIdx.x; k < passes * BINS; k += SW_KH_THREADS) {
@@ -168,7 +322,7 @@ struct SweepPassCfg {
 // sends the whole warp back to poll the same window.  A thread-per-digit walk (one predecessor per
 // L2 round trip) made the first wave of CTAs, which all start together, wait ~R/2 round trips.
 template <int M>
-__device__ __forceinline__ void sw_lookback(const uint32_t *status, int bins, uint32_t tile, int dq,
+__device__ __forceinline__ void sw_lookback(const uint32_t *status, int bins, uint32_t tile, int floor_tile, int dq,
                                             uint32_t (&before)[4], uint32_t *err) {
     const int lane = threadIdx.x & 31, grp = lane >> 3;
     uint32_t sum[4] = {0, 0, 0, 0};
@@ -180,8 +334,8 @@ __device__ __forceinline__ void sw_lookback(const uint32_t *status, int bins, ui
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             const int t = wstart - (grp * M + m);
-            s[m] = t >= 0 ? ld_volatile_v4(status + (size_t)t * bins + dq)
-                          : make_uint4(SW_PREFIX, SW_PREFIX, SW_PREFIX, SW_PREFIX);   // before tile 0: nothing
+            s[m] = t >= floor_tile ? ld_volatile_v4(status + (size_t)t * bins + dq)
+                          : make_uint4(SW_PREFIX, SW_PREFIX, SW_PREFIX, SW_PREFIX);   // below the floor: nothing
         }
         uint32_t wsum[4] = {0, 0, 0, 0}, wdone = 0, winv = 0;
 #pragma unroll
@@ -239,10 +393,45 @@ __device__ __forceinline__ void sw_lookback(const uint32_t *status, int bins, ui
     for (int i = 0; i < 4; ++i) before[i] = sum[i];
 }
 
+// Sum of the counts the earlier tiles of this tile's group published for 32 digits (same lane layout
+// as sw_lookback with M = 4: one step covers the whole group).  Tile words only ever carry counts.
+__device__ __forceinline__ void sw_group_sum(const uint32_t *status, int bins, uint32_t tile, int floor_tile, int dq,
+                                             uint32_t (&sum)[4], uint32_t *err) {
+    const int lane = threadIdx.x & 31, grp = lane >> 3;
+    int spins = 0;
+    while (true) {
+        uint32_t acc[4] = {0, 0, 0, 0};
+        bool ready = true;
+#pragma unroll
+        for (int m = 0; m < SW_GROUP / 4; ++m) {
+            const int t = (int)tile - 1 - (grp * (SW_GROUP / 4) + m);
+            if (t >= floor_tile) {
+                const uint4 v = ld_volatile_v4(status + (size_t)t * bins + dq);
+                ready = ready && (v.x >> 30) && (v.y >> 30) && (v.z >> 30) && (v.w >> 30);
+                acc[0] += v.x & SW_VALUE; acc[1] += v.y & SW_VALUE; acc[2] += v.z & SW_VALUE; acc[3] += v.w & SW_VALUE;
+            }
+        }
+        if (__all_sync(0xffffffffu, ready)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+                acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+                sum[i] = acc[i];
+            }
+            return;
+        }
+        if (++spins >= SW_SPIN_LIMIT) {
+            if (lane == 0) atomicExch(err, 1u);
+            return;
+        }
+    }
+}
+
 template <int BITS, int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS, (BITS <= 8 ? 3 : 2))
 sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n, int shift,
-        const uint32_t *__restrict__ gbase, uint32_t *status, uint32_t *ticket, uint32_t *err) {
+        const uint32_t *__restrict__ gbase, uint32_t *status, uint32_t *gstatus, uint32_t *gacc, uint32_t *gdone,
+        int n_tiles, uint32_t *ticket, uint32_t *err) {
     using Cfg = SweepPassCfg<BITS, THREADS, ITEMS>;
     constexpr int BINS = Cfg::BINS, WARPS = Cfg::WARPS, TILE = Cfg::TILE, DPT = Cfg::DPT;
     extern __shared__ __align__(16) uint8_t sw_smem[];
@@ -251,12 +440,15 @@ sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n, int 
     uint32_t *tile_excl = wh + WARPS * BINS;                      // [BINS] first tile-local slot of a digit
     uint32_t *tile_cnt = tile_excl + BINS;                        // [BINS] elements of a digit in this tile
     uint32_t *gdelta = tile_cnt + BINS;                           // [BINS] global slot = gdelta + tile-local slot
-    __shared__ uint32_t s_tile, warp_tot[33];
+    __shared__ uint32_t s_tile, s_closer, warp_tot[33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);   // tiles are taken in the order CTAs start running
     for (int k = threadIdx.x; k < WARPS * BINS; k += THREADS) wh[k] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
+    const uint32_t group = tile / SW_GROUP;
+    const int group_first = (int)(group * SW_GROUP);
+    const uint32_t group_tiles = (uint32_t)min(SW_GROUP, n_tiles - group_first);
     const int tbase = (int)tile * TILE;
     const int wbase = tbase + warp * (32 * ITEMS);   // warp-blocked: warp w owns 32*ITEMS consecutive words
     uint32_t *mywh = wh + warp * BINS;
@@ -270,8 +462,16 @@ sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n, int 
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const bool valid = wbase + k * 32 + lane < n;
-        const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & (BINS - 1)) : (uint32_t)(BINS + lane);
-        const uint32_t mask = __match_any_sync(0xffffffffu, d);
+        const uint32_t d = (uint32_t)(key[k] >> shift) & (BINS - 1);
+        // lanes holding the same digit, from one ballot per digit bit: MATCH.ANY measured ~35 cycles of
+        // a per-SM unit per warp instruction (a 57 us floor per pass on 14.7 M words), BITS ballots do not
+        uint32_t mask = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int b = 0; b < BITS; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t v = __ballot_sync(0xffffffffu, bit);
+            mask &= bit ? v : ~v;
+        }
         const int leader = __ffs(mask) - 1;
         const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
         uint32_t prev = 0;
@@ -299,8 +499,9 @@ sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n, int 
         cnt[j] = run;
         tsum += run;
         tile_cnt[d] = run;
-        // let the successors see this tile's counts as early as possible
-        st_volatile_u32(status + (size_t)tile * BINS + d, (tile == 0 ? SW_PREFIX : SW_AGG) | run);
+        // let the successors see this tile's counts as early as possible, and add them to the group's
+        st_volatile_u32(status + (size_t)tile * BINS + d, SW_AGG | run);
+        if (run) atomicAdd(gacc + (size_t)group * BINS + d, run);
     }
     uint32_t total;
     uint32_t ex = block_exclusive_scan(tsum, warp_tot, total);
@@ -319,18 +520,43 @@ sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n, int 
             skeys[tile_excl[d] + mywh[d] + local[k]] = key[k];
         }
     }
-    for (int group = warp; group < BINS / 32; group += WARPS) {
-        const int dq = group * 32 + 4 * (lane & 7);
-        uint32_t before[4] = {0, 0, 0, 0};
-        if (tile > 0) sw_lookback<4>(status, BINS, tile, dq, before, err);
+    // The tile that completes its group publishes the group's totals (tile_cnt becomes the group's):
+    // the group-level status words are what later tiles walk over, 16 tiles per word.
+    // (every thread's counts and group sums happen-before the barrier above; one cumulative fence
+    // then orders them before this tile is counted as done)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_closer = (atomicAdd(gdone + group, 1u) + 1u == group_tiles) ? 1u : 0u;
+    }
+    __syncthreads();
+    const bool closer = s_closer != 0;
+    if (closer) {
+        __threadfence();
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            const int d = threadIdx.x * DPT + j;
+            const uint32_t tot = ld_volatile_u32(gacc + (size_t)group * BINS + d);
+            tile_cnt[d] = tot;
+            st_volatile_u32(gstatus + (size_t)group * BINS + d, (group == 0 ? SW_PREFIX : SW_AGG) | tot);
+        }
+        __syncthreads();
+    }
+    // digits before this tile = the group's earlier tiles (one window, it stops at the group's first
+    // tile) + everything before the group (a walk over group words: 16 groups = 256 tiles per step)
+    for (int g32 = warp; g32 < BINS / 32; g32 += WARPS) {
+        const int dq = g32 * 32 + 4 * (lane & 7);
+        uint32_t in_group[4] = {0, 0, 0, 0}, before_group[4] = {0, 0, 0, 0};
+        if ((int)tile > group_first) sw_group_sum(status, BINS, tile, group_first, dq, in_group, err);
+        if (group > 0) sw_lookback<4>(gstatus, BINS, group, 0, dq, before_group, err);
         if (lane < 8) {
             uint32_t pub[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                gdelta[dq + i] = gbase[dq + i] + before[i] - tile_excl[dq + i];
-                pub[i] = SW_PREFIX | ((before[i] + tile_cnt[dq + i]) & SW_VALUE);
+                gdelta[dq + i] = gbase[dq + i] + before_group[i] + in_group[i] - tile_excl[dq + i];
+                pub[i] = SW_PREFIX | ((before_group[i] + tile_cnt[dq + i]) & SW_VALUE);
             }
-            if (tile > 0) st_volatile_v4(status + (size_t)tile * BINS + dq, make_uint4(pub[0], pub[1], pub[2], pub[3]));
+            if (closer && group > 0)
+                st_volatile_v4(gstatus + (size_t)group * BINS + dq, make_uint4(pub[0], pub[1], pub[2], pub[3]));
         }
     }
     __syncthreads();
@@ -443,21 +669,39 @@ sw_chunk_scan(const uint64_t *__restrict__ info, int n_chunks, uint32_t *__restr
 // ---- 5. segmented sums -> records -------------------------------------------------------
 __device__ __forceinline__ void sw_emit(int16_t *__restrict__ out, uint32_t vid, const uint32_t (&a)[7], uint64_t key,
                                         const SweepGeom &g) {
-    const uint64_t m = (1ull << g.bits) - 1;
-    const int kx = (int)(key & m) + g.kmin, ky = (int)((key >> g.bits) & m) + g.kmin,
-              kz = (int)((key >> (2 * g.bits)) & m) + g.kmin;
+    // exact: key * d < 2^64 (key < 2^48, d < 2^16)
+    const uint64_t t = g.mdx ? __umul64hi(key, g.mdx) : key;           // key / dx
+    const uint64_t u = g.mdy ? __umul64hi(t, g.mdy) : t;               // key / (dx * dy)
+    const int qx = (int)(key - t * g.dx) + g.x0, qy = (int)(t - u * g.dy) + g.y0, qz = (int)u + g.z0;
     const uint32_t cnt = a[6];
+    // floor(a / cnt) for six sums: one reciprocal, then a multiply, a truncation and a +-1 fix-up
+    // each.  a / cnt <= max(255, leaf - 1) < 2^15, so the float product is off by far less than 1.
+    const float r = __frcp_rn((float)cnt);
+    uint32_t q[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        // a + cnt < 2^32 (the ABI bounds n * max(256, leaf)), so the remainder is exact modulo 2^32
+        uint32_t e = (uint32_t)__float2int_rz(__fmul_rn((float)a[k], r));
+        const int rem = (int)(a[k] - e * cnt);
+        if (rem < 0) --e;
+        else if ((uint32_t)rem >= cnt) ++e;
+        q[k] = e;
+    }
     int16_t *o = out + 5 * (size_t)vid;
-    o[0] = (int16_t)(g.leaf * kx + (int)(a[0] / cnt));
-    o[1] = (int16_t)(g.leaf * ky + (int)(a[1] / cnt));
-    o[2] = (int16_t)(g.leaf * kz + (int)(a[2] / cnt));
-    o[3] = (int16_t)((a[3] / cnt) | ((a[4] / cnt) << 8));
-    o[4] = (int16_t)(a[5] / cnt);
+    o[0] = (int16_t)(g.leaf * qx - g.bias + (int)q[0]);
+    o[1] = (int16_t)(g.leaf * qy - g.bias + (int)q[1]);
+    o[2] = (int16_t)(g.leaf * qz - g.bias + (int)q[2]);
+    o[3] = (int16_t)(q[3] | (q[4] << 8));
+    o[4] = (int16_t)q[5];
 }
 
 // slots[c] = 8 words: 7 sums of chunk c's last voxel when it continues into later chunks, word 7 =
 // "finalise me"; slotkey[c] = that voxel's key.  All the chunk's sort words and gather words are
 // requested before the first round is reduced (a round is one dependent DRAM round trip otherwise).
+// PACKED (off_bits <= 5, i.e. leaf <= 32): the seven running sums of a round fit three words
+// (3 x 10-bit offset sums | R 13, G 13, count 6 | B 13), so the segmented scan moves 3 registers
+// per step instead of 7.
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
 sw_reduce(const uint64_t *__restrict__ sorted, int n, const uint64_t *__restrict__ pay, SweepGeom g, int n_chunks,
           const uint32_t *__restrict__ chunk_off, const uint32_t *__restrict__ ownerpos,
@@ -485,8 +729,9 @@ sw_reduce(const uint64_t *__restrict__ sorted, int n, const uint64_t *__restrict
     uint64_t before = base > 0 ? sorted[base - 1] >> g.idx_bits : 0;
     // the open voxel carried from round to round (warp-uniform)
     uint32_t carry[7] = {0, 0, 0, 0, 0, 0, 0};
-    bool carry_has_head = false;
+    bool carry_has_head = false, carry_closed = false;
     uint64_t carry_key = before;
+    const uint64_t next_chunk_key = base + SW_CHUNK < n ? sorted[base + SW_CHUNK] >> g.idx_bits : 0;
 #pragma unroll
     for (int r = 0; r < SW_CHUNK_ROUNDS; ++r) {
         const int e = base + r * 32 + lane;
@@ -496,76 +741,106 @@ sw_reduce(const uint64_t *__restrict__ sorted, int n, const uint64_t *__restrict
         if (lane == 0) prev = before;
         const bool head = valid && (e == 0 || key != prev);
         const uint32_t hm = __ballot_sync(0xffffffffu, head);
-        // the carried voxel ended exactly at the previous round's last lane
-        if ((hm & 1u) && r > 0 && lane == 0) {
-            if (carry_has_head) {
-                sw_emit(out, run_vid, carry, carry_key, g);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 7; ++k) atomicAdd(slots + 8 * (size_t)owner + k, carry[k]);
-            }
-        }
         const uint32_t le = hm & (0xffffffffu >> (31 - lane));
         const uint32_t vid = run_vid + __popc(le);
         const bool started_here = le != 0;
         const int seg_start = started_here ? 31 - __clz(le) : 0;
         uint32_t v[7] = {0, 0, 0, 0, 0, 0, 0};
-        if (valid) {
-            const uint32_t lo = (uint32_t)pw[r];
-            const uint64_t offs = pw[r] >> 24;
-            v[0] = (uint32_t)offs & om;
-            v[1] = (uint32_t)(offs >> g.off_bits) & om;
-            v[2] = (uint32_t)(offs >> (2 * g.off_bits)) & om;
-            v[3] = lo & 0xFF; v[4] = (lo >> 8) & 0xFF; v[5] = (lo >> 16) & 0xFF; v[6] = 1;
-        }
-        // warp-shuffle segmented inclusive scan
+        if (PACKED) {
+            uint32_t A = 0, B = 0, Cc = 0;
+            if (valid) {
+                const uint32_t lo = (uint32_t)pw[r];
+                const uint32_t offs = (uint32_t)(pw[r] >> 24);
+                A = (offs & om) | (((offs >> g.off_bits) & om) << 10) | (((offs >> (2 * g.off_bits)) & om) << 20);
+                B = (lo & 0xFF) | (((lo >> 8) & 0xFF) << 13) | (1u << 26);
+                Cc = (lo >> 16) & 0xFF;
+            }
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o[7];
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t a = __shfl_up_sync(0xffffffffu, A, d), b = __shfl_up_sync(0xffffffffu, B, d),
+                               c = __shfl_up_sync(0xffffffffu, Cc, d);
+                if (lane >= d && lane - d >= seg_start) { A += a; B += b; Cc += c; }
+            }
+            v[0] = A & 1023u; v[1] = (A >> 10) & 1023u; v[2] = A >> 20;
+            v[3] = B & 8191u; v[4] = (B >> 13) & 8191u; v[6] = B >> 26; v[5] = Cc;
+        } else {
+            if (valid) {
+                const uint32_t lo = (uint32_t)pw[r];
+                const uint64_t offs = pw[r] >> 24;
+                v[0] = (uint32_t)offs & om;
+                v[1] = (uint32_t)(offs >> g.off_bits) & om;
+                v[2] = (uint32_t)(offs >> (2 * g.off_bits)) & om;
+                v[3] = lo & 0xFF; v[4] = (lo >> 8) & 0xFF; v[5] = (lo >> 16) & 0xFF; v[6] = 1;
+            }
+            // warp-shuffle segmented inclusive scan
 #pragma unroll
-            for (int k = 0; k < 7; ++k) o[k] = __shfl_up_sync(0xffffffffu, v[k], d);
-            if (lane >= d && lane - d >= seg_start) {
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o[7];
 #pragma unroll
-                for (int k = 0; k < 7; ++k) v[k] += o[k];
+                for (int k = 0; k < 7; ++k) o[k] = __shfl_up_sync(0xffffffffu, v[k], d);
+                if (lane >= d && lane - d >= seg_start) {
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) v[k] += o[k];
+                }
             }
         }
         // key of the voxel a lane belongs to (its own key, except on the padding lanes past n)
         const uint64_t key_at_start = __shfl_sync(0xffffffffu, key, seg_start);
         const uint64_t seg_key = started_here ? key_at_start : carry_key;
-        const bool is_end = lane < 31 && ((hm >> (lane + 1)) & 1u);
+        // lane 31's voxel ends with this round when the next element (next round, or next chunk) starts
+        // a new voxel or does not exist; every voxel end of the round goes through ONE emit site
+        // (divergent copies of the emit were each paid in full by the whole warp)
+        uint64_t nxt_key;
+        bool nxt_valid;
+        if (r + 1 < SW_CHUNK_ROUNDS) {
+            nxt_key = __shfl_sync(0xffffffffu, word[r + 1 < SW_CHUNK_ROUNDS ? r + 1 : r] >> g.idx_bits, 0);
+            nxt_valid = base + (r + 1) * 32 < n;
+        } else {
+            nxt_key = next_chunk_key;
+            nxt_valid = base + SW_CHUNK < n;
+        }
+        const bool end31 = valid && (!nxt_valid || nxt_key != key);
+        const bool is_end = lane < 31 ? (((hm >> (lane + 1)) & 1u) != 0) : end31;
+        const bool whole = started_here || carry_has_head;     // the voxel's head is in this chunk
         if (is_end) {
-            if (started_here) {
-                sw_emit(out, vid, v, seg_key, g);
+            uint32_t tot[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) tot[k] = started_here ? v[k] : carry[k] + v[k];
+            if (whole) {
+                sw_emit(out, vid, tot, seg_key, g);
             } else {
-                uint32_t tot[7];
 #pragma unroll
-                for (int k = 0; k < 7; ++k) tot[k] = carry[k] + v[k];
-                if (carry_has_head) {
-                    sw_emit(out, vid, tot, seg_key, g);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) atomicAdd(slots + 8 * (size_t)owner + k, tot[k]);
-                }
+                for (int k = 0; k < 7; ++k) atomicAdd(slots + 8 * (size_t)owner + k, tot[k]);
             }
         }
-        // lane 31's voxel stays open
-        const bool l31_started = __shfl_sync(0xffffffffu, (int)started_here, 31) != 0;
-        const uint64_t l31_key = __shfl_sync(0xffffffffu, seg_key, 31);
+        if (__shfl_sync(0xffffffffu, (int)end31, 31)) {
+            // nothing stays open
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            const uint32_t t = __shfl_sync(0xffffffffu, v[k], 31);
-            carry[k] = l31_started ? t : carry[k] + t;
-        }
-        if (l31_started) {
-            carry_has_head = true;
-            carry_key = l31_key;
+            for (int k = 0; k < 7; ++k) carry[k] = 0;
+            carry_has_head = false;
+            carry_closed = true;
+        } else if (base + r * 32 < n) {
+            // lane 31's voxel stays open
+            const bool l31_started = __shfl_sync(0xffffffffu, (int)started_here, 31) != 0;
+            const uint64_t l31_key = __shfl_sync(0xffffffffu, seg_key, 31);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const uint32_t t = __shfl_sync(0xffffffffu, v[k], 31);
+                carry[k] = l31_started ? t : carry[k] + t;
+            }
+            if (l31_started) {
+                carry_has_head = true;
+                carry_key = l31_key;
+            }
+            carry_closed = false;
         }
         run_vid += __popc(hm);
         before = __shfl_sync(0xffffffffu, key, 31);
     }
-    // the chunk's last voxel: complete if the next chunk starts with a head (or there is none)
-    if (lane == 0) {
-        const bool complete = base + SW_CHUNK >= n || (sorted[base + SW_CHUNK] >> g.idx_bits) != carry_key;
+    // a voxel still open after the last round: it runs into the next chunk, or the data ended inside
+    // a round (then it is complete)
+    if (lane == 0 && !carry_closed) {
+        const bool complete = base + SW_CHUNK >= n || next_chunk_key != carry_key;
         if (carry_has_head && complete) {
             sw_emit(out, run_vid, carry, carry_key, g);
         } else {
@@ -594,20 +869,24 @@ sw_finalize_open(const uint64_t *__restrict__ info, const uint32_t *__restrict__
 }
 
 // ---- host side ----------------------------------------------------------------------------
-inline int sweep_idx_bits(int n) {
+inline int sweep_bits_for(long long count) {    // bits needed for values 0 .. count-1 (at least 1)
     int b = 1;
-    while (b < 31 && (1ll << b) < (long long)n) ++b;
+    while (b < 62 && (1ll << b) < count) ++b;
     return b;
 }
 
-inline bool sweep_fits(int n, int leaf) {
-    const int kmin = -(32768 + leaf - 1) / leaf, kmax = 32767 / leaf;
-    int bits = 1;
-    while ((1 << bits) < (kmax - kmin + 1)) ++bits;
-    int ob = 1;
-    while ((1 << ob) < leaf) ++ob;
-    return 3 * bits + sweep_idx_bits(n) <= 64 && 24 + 3 * ob <= 64 && n < (1 << 30);
+inline SweepGeom sweep_base_geom(int leaf) {
+    SweepGeom g{};
+    g.leaf = leaf;
+    g.K = (32768 + leaf - 1) / leaf;
+    g.bias = leaf * g.K;
+    g.magic = ((1ull << 40) / (unsigned long long)leaf) + 1ull;
+    g.off_bits = sweep_bits_for(leaf);
+    g.z_lo = 0;
+    g.z_hi = 0x7FFFFFFF;
+    return g;
 }
+inline int sweep_zbins(const SweepGeom &g) { return (32767 + g.bias) / g.leaf + 1; }
 
 template <int BITS, int THREADS, int ITEMS>
 inline int sweep_configure() {
@@ -617,37 +896,7 @@ inline int sweep_configure() {
     return 0;
 }
 
-// Returns the voxel count (>= 0), -2 on a CUDA error, -3 on allocation failure, -4 when the sort
-// word does not fit (the caller picks the pair sort then).  Everything is queued before the one
-// synchronisation that brings the count back.
-template <int BITS, int THREADS, int ITEMS>
-inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int leaf, int16_t *out, cudaStream_t cs,
-                             int sm_count) {
-    using Cfg = SweepPassCfg<BITS, THREADS, ITEMS>;
-    constexpr int BINS = Cfg::BINS;
-    if (!sweep_fits(n, leaf)) return -4;
-    SweepGeom g;
-    g.leaf = leaf;
-    g.kmin = -(32768 + leaf - 1) / leaf;
-    const int kmax = 32767 / leaf;
-    g.bits = 1;
-    while ((1 << g.bits) < (kmax - g.kmin + 1)) ++g.bits;
-    g.idx_bits = sweep_idx_bits(n);
-    g.off_bits = 1;
-    while ((1 << g.off_bits) < leaf) ++g.off_bits;
-    const int passes = (3 * g.bits + BITS - 1) / BITS;
-    const int n_tiles = (n + Cfg::TILE - 1) / Cfg::TILE;
-    const int n_chunks = (n + SW_CHUNK - 1) / SW_CHUNK;
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    // [words0][words1][pay] | zeroed: [ghist][tickets][err][status][slots] | [info][chunk_off][ownerpos][slotkey][nv]
-    const size_t o_w0 = 0, o_w1 = o_w0 + al((size_t)n * 8), o_pay = o_w1 + al((size_t)n * 8),
-                 o_zero = o_pay + al((size_t)n * 8),
-                 o_ghist = o_zero, o_ticket = o_ghist + al((size_t)passes * BINS * 4), o_err = o_ticket + al(64),
-                 o_status = o_err + al(64), o_slots = o_status + al((size_t)passes * n_tiles * BINS * 4),
-                 o_zero_end = o_slots + al((size_t)n_chunks * 32),
-                 o_info = o_zero_end, o_off = o_info + al((size_t)n_chunks * 8), o_owner = o_off + al((size_t)n_chunks * 4),
-                 o_skey = o_owner + al((size_t)n_chunks * 4), o_nv = o_skey + al((size_t)n_chunks * 8),
-                 total = o_nv + al(64);
+inline int sweep_reserve(VoxelScratch &s, size_t total) {
     if (total > s.cap) {
         cudaFree(s.buf);
         s.buf = nullptr; s.cap = 0;
@@ -655,28 +904,146 @@ inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int lea
         s.cap = total;
     }
     if (!s.h_count && cudaHostAlloc(&s.h_count, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return -3; }
-    uint64_t *w0 = (uint64_t *)(s.buf + o_w0), *w1 = (uint64_t *)(s.buf + o_w1), *pay = (uint64_t *)(s.buf + o_pay);
-    uint32_t *ghist = (uint32_t *)(s.buf + o_ghist), *ticket = (uint32_t *)(s.buf + o_ticket),
-             *err = (uint32_t *)(s.buf + o_err), *status = (uint32_t *)(s.buf + o_status),
-             *slots = (uint32_t *)(s.buf + o_slots), *chunk_off = (uint32_t *)(s.buf + o_off),
-             *ownerpos = (uint32_t *)(s.buf + o_owner);
-    uint64_t *info = (uint64_t *)(s.buf + o_info), *slotkey = (uint64_t *)(s.buf + o_skey);
-    int32_t *nv_dev = (int32_t *)(s.buf + o_nv);
-    if (cudaMemsetAsync(s.buf + o_zero, 0, o_zero_end - o_zero, cs) != cudaSuccess) return -2;
+    return 0;
+}
+
+// Cuts the qz axis into n_slabs slabs of (nearly) equal population.  kz_splits[0 .. n_slabs] are
+// plane indices floor(z / leaf): slab r holds kz_splits[r] <= floor(z / leaf) < kz_splits[r + 1];
+// slab_points[r] (optional) is its population.  Identical inputs give identical cuts, so ranks
+// that hold the same stitched cloud agree on the plan without talking to each other.
+inline int voxel_slab_plan(VoxelScratch &s, const int16_t *rec, int n, int leaf, int n_slabs, int32_t *kz_splits,
+                           int32_t *slab_points, cudaStream_t cs, int sm_count) {
+    SweepGeom g = sweep_base_geom(leaf);
+    const int zbins = sweep_zbins(g);
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t total = al(64) + al((size_t)zbins * 4);
+    int rc = sweep_reserve(s, total);
+    if (rc) return rc;
+    uint32_t *bounds = (uint32_t *)s.buf, *zhist = (uint32_t *)(s.buf + al(64));
+    if (cudaMemsetAsync(s.buf, 0, total, cs) != cudaSuccess || cudaMemsetAsync(bounds, 0xFF, 12, cs) != cudaSuccess) return -2;
+    const int in_smem = (size_t)zbins * 4 <= 40 * 1024 ? 1 : 0;
+    const int tiles = (n + SW_KH_TILE - 1) / SW_KH_TILE;
+    const int grid = std::max(1, std::min(tiles, std::max(1, sm_count) * 8));
+    sw_bounds<true><<<grid, SW_KH_THREADS, in_smem ? (size_t)zbins * 4 : 0, cs>>>(rec, n, g, bounds, zhist, zbins, in_smem);
+    std::vector<uint32_t> h(zbins);
+    if (cudaMemcpyAsync(h.data(), zhist, (size_t)zbins * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return -2;
+    if (cudaStreamSynchronize(cs) != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
+    int lo = 0, hi = zbins - 1;
+    while (lo < zbins && !h[lo]) ++lo;
+    while (hi >= 0 && !h[hi]) --hi;
+    if (lo > hi) { lo = 0; hi = -1; }     // no points
+    // slab r ends at the first plane where the running count reaches (r + 1) * n / n_slabs
+    long long cum = 0;
+    int q = lo;
+    kz_splits[0] = lo - g.K;
+    for (int r = 0; r < n_slabs; ++r) {
+        const long long target = (long long)n * (r + 1) / n_slabs;
+        const long long start = cum;
+        while (q <= hi && (cum < target || r == n_slabs - 1)) cum += h[q++];
+        kz_splits[r + 1] = q - g.K;
+        if (slab_points) slab_points[r] = (int32_t)(cum - start);
+    }
+    return 0;
+}
+
+// Returns the voxel count (>= 0), -2 on a CUDA error, -3 on allocation failure, -4 when the sort
+// word does not fit (the caller picks the pair sort then).  Two host synchronisations: the occupied
+// box has to reach the host before the key layout is fixed, and the count at the end.
+// slab: merge only the points with kz_lo <= floor(z / leaf) < kz_hi.
+template <int BITS, int THREADS, int ITEMS>
+inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int leaf, int16_t *out, cudaStream_t cs,
+                             int sm_count, bool slab = false, int kz_lo = 0, int kz_hi = 0) {
+    using Cfg = SweepPassCfg<BITS, THREADS, ITEMS>;
+    constexpr int BINS = Cfg::BINS;
+    SweepGeom g = sweep_base_geom(leaf);
+    const int zbins = sweep_zbins(g);
+    if (24 + 3 * g.off_bits > 64 || n >= (1 << 30)) return -4;
+    if (slab) {
+        g.z_lo = std::max(0, std::min(zbins, kz_lo + g.K));
+        g.z_hi = std::max(0, std::min(zbins, kz_hi + g.K));
+        if (g.z_lo >= g.z_hi) return 0;
+    }
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    // sized for the worst case (every point inside, full-range keys) so that nothing is allocated
+    // between the two phases:
+    // [bounds][words0][words1][pay] | zeroed: [ghist][tickets][err][slot counter][group status, sums,
+    // done counters][status][slots] |
+    // [info][chunk_off][ownerpos][slotkey][nv]
+    const int passes_max = (3 * sweep_bits_for(zbins) + BITS - 1) / BITS;
+    const int tiles_max = (n + Cfg::TILE - 1) / Cfg::TILE, chunks_max = (n + SW_CHUNK - 1) / SW_CHUNK;
+    const int groups_max = (tiles_max + SW_GROUP - 1) / SW_GROUP;
+    const size_t o_bounds = 0, o_w0 = al(64), o_w1 = o_w0 + al((size_t)n * 8), o_pay = o_w1 + al((size_t)n * 8),
+                 o_zero = o_pay + al((size_t)n * 8),
+                 o_ghist = o_zero, o_ticket = o_ghist + al((size_t)passes_max * BINS * 4), o_err = o_ticket + al(64),
+                 o_cnt = o_err + al(64), o_gstat = o_cnt + al(64),
+                 o_gacc = o_gstat + al((size_t)passes_max * groups_max * BINS * 4),
+                 o_gdone = o_gacc + al((size_t)passes_max * groups_max * BINS * 4),
+                 o_status = o_gdone + al((size_t)passes_max * groups_max * 4),
+                 o_slots = o_status + al((size_t)passes_max * tiles_max * BINS * 4),
+                 o_zero_end = o_slots + al((size_t)chunks_max * 32),
+                 o_info = o_zero_end, o_off = o_info + al((size_t)chunks_max * 8), o_owner = o_off + al((size_t)chunks_max * 4),
+                 o_skey = o_owner + al((size_t)chunks_max * 4), o_nv = o_skey + al((size_t)chunks_max * 8),
+                 total = o_nv + al(64);
+    int rc = sweep_reserve(s, total);
+    if (rc) return rc;
+    // ---- phase 0: occupied box (and the slab's population)
+    uint32_t *bounds = (uint32_t *)(s.buf + o_bounds);
+    if (cudaMemsetAsync(bounds, 0, 64, cs) != cudaSuccess || cudaMemsetAsync(bounds, 0xFF, 12, cs) != cudaSuccess) return -2;
     const int kh_tiles = (n + SW_KH_TILE - 1) / SW_KH_TILE;
     const int kh_grid = std::min(kh_tiles, std::max(1, sm_count) * 8);
-    sw_keys_hist<BITS><<<kh_grid, SW_KH_THREADS, (size_t)passes * BINS * 4, cs>>>(rec, n, g, passes, w0, pay, ghist);
+    sw_bounds<false><<<kh_grid, SW_KH_THREADS, 0, cs>>>(rec, n, g, bounds, nullptr, 0, 0);
+    uint32_t *hb = (uint32_t *)s.h_count;
+    if (cudaMemcpyAsync(hb, bounds, 28, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return -2;
+    if (cudaStreamSynchronize(cs) != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
+    const int m = (int)hb[6];         // points to sort
+    if (m == 0) return 0;
+    if (m > n) return -2;
+    g.x0 = (int)hb[0]; g.y0 = (int)hb[1]; g.z0 = (int)hb[2];
+    g.dx = hb[3] - hb[0] + 1;
+    g.dy = hb[4] - hb[1] + 1;
+    g.mdx = g.dx > 1 ? ~0ull / g.dx + 1ull : 0ull;
+    g.mdy = g.dy > 1 ? ~0ull / g.dy + 1ull : 0ull;
+    const long long dz = (long long)hb[5] - hb[2] + 1;
+    g.idx_bits = sweep_bits_for(slab ? m : n);
+    const int key_bits = sweep_bits_for((long long)g.dx * g.dy * dz);     // <= 6554^3 < 2^39 at leaf 10; < 2^48 always
+    if (key_bits + g.idx_bits > 64) return -4;
+    // the multiply-high divisions in sw_emit are exact while key * d stays below 2^64
+    if ((double)g.dx * g.dy * (double)dz * (double)std::max(g.dx, g.dy) >= 9.0e18) return -4;
+    const int passes = (key_bits + BITS - 1) / BITS;
+    const int n_tiles = (m + Cfg::TILE - 1) / Cfg::TILE;
+    const int n_chunks = (m + SW_CHUNK - 1) / SW_CHUNK;
+    uint64_t *w0 = (uint64_t *)(s.buf + o_w0), *w1 = (uint64_t *)(s.buf + o_w1), *pay = (uint64_t *)(s.buf + o_pay);
+    uint32_t *ghist = (uint32_t *)(s.buf + o_ghist), *ticket = (uint32_t *)(s.buf + o_ticket),
+             *err = (uint32_t *)(s.buf + o_err), *slot_counter = (uint32_t *)(s.buf + o_cnt),
+             *status = (uint32_t *)(s.buf + o_status), *slots = (uint32_t *)(s.buf + o_slots),
+             *gstatus = (uint32_t *)(s.buf + o_gstat), *gacc = (uint32_t *)(s.buf + o_gacc),
+             *gdone = (uint32_t *)(s.buf + o_gdone),
+             *chunk_off = (uint32_t *)(s.buf + o_off), *ownerpos = (uint32_t *)(s.buf + o_owner);
+    uint64_t *info = (uint64_t *)(s.buf + o_info), *slotkey = (uint64_t *)(s.buf + o_skey);
+    int32_t *nv_dev = (int32_t *)(s.buf + o_nv);
+    // only what this run touches is cleared: [ghist .. status of `passes` x `n_tiles`] and the slots
+    if (cudaMemsetAsync(s.buf + o_zero, 0, (o_status - o_zero) + al((size_t)passes * n_tiles * BINS * 4), cs) != cudaSuccess ||
+        cudaMemsetAsync(slots, 0, (size_t)n_chunks * 32, cs) != cudaSuccess)
+        return -2;
+    if (slab)
+        sw_keys_hist<BITS, true><<<kh_grid, SW_KH_THREADS, (size_t)passes * BINS * 4, cs>>>(rec, n, g, passes, w0, pay, ghist, slot_counter);
+    else
+        sw_keys_hist<BITS, false><<<kh_grid, SW_KH_THREADS, (size_t)passes * BINS * 4, cs>>>(rec, n, g, passes, w0, pay, ghist, slot_counter);
     sw_hist_scan<BITS><<<passes, BINS, 0, cs>>>(ghist);
     for (int p = 0; p < passes; ++p) {
         sw_pass<BITS, THREADS, ITEMS><<<n_tiles, THREADS, Cfg::SMEM, cs>>>(
-            w0, w1, n, g.idx_bits + p * BITS, ghist + (size_t)p * BINS, status + (size_t)p * n_tiles * BINS,
-            ticket + p, err);
+            w0, w1, m, g.idx_bits + p * BITS, ghist + (size_t)p * BINS, status + (size_t)p * n_tiles * BINS,
+            gstatus + (size_t)p * groups_max * BINS, gacc + (size_t)p * groups_max * BINS,
+            gdone + (size_t)p * groups_max, n_tiles, ticket + p, err);
         std::swap(w0, w1);
     }
     const int cblocks = (n_chunks + 7) / 8;
-    sw_chunk_heads<<<cblocks, 256, 0, cs>>>(w0, n, g.idx_bits, n_chunks, info);
+    sw_chunk_heads<<<cblocks, 256, 0, cs>>>(w0, m, g.idx_bits, n_chunks, info);
     sw_chunk_scan<<<1, 1024, 0, cs>>>(info, n_chunks, chunk_off, ownerpos, nv_dev);
-    sw_reduce<<<cblocks, 256, 0, cs>>>(w0, n, pay, g, n_chunks, chunk_off, ownerpos, slots, slotkey, out);
+    if (g.off_bits <= 5)
+        sw_reduce<true><<<cblocks, 256, 0, cs>>>(w0, m, pay, g, n_chunks, chunk_off, ownerpos, slots, slotkey, out);
+    else
+        sw_reduce<false><<<cblocks, 256, 0, cs>>>(w0, m, pay, g, n_chunks, chunk_off, ownerpos, slots, slotkey, out);
     sw_finalize_open<<<(n_chunks + 255) / 256, 256, 0, cs>>>(info, chunk_off, slots, slotkey, n_chunks, g, out);
     if (cudaMemcpyAsync(s.h_count, nv_dev, 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return -2;
     if (cudaMemcpyAsync(s.h_count + 1, err, 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return -2;
@@ -684,7 +1051,7 @@ inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int lea
     if (cudaGetLastError() != cudaSuccess) return -2;
     if (s.h_count[1] != 0) return -2;           // a look-back gave up waiting
     const int nv = s.h_count[0];
-    if (nv < 1 || nv > n) return -2;
+    if (nv < 1 || nv > m) return -2;
     return nv;
 }
 

@@ -212,3 +212,36 @@ class SymmetricFrameSet:
     def barrier(self):
         """All ranks have finished reading each other's frames (call before overwriting them)."""
         self.handle.barrier()
+
+
+def sharded_voxel_merge(ctx, records_ptr, n, leaf_mm, rank, world, out, cuda_stream=0, gather=True, group=None):
+    """Voxel merge of a stitched cloud that every rank holds, sharded by z-slab.
+
+    Every rank computes the same equal-population cuts of the grid along z from its own copy of the
+    records (no communication), merges slab ``rank`` only -- 1/world of the sort work -- into
+    ``out`` (int16 tensor, capacity n * 5) and, with ``gather``, the slabs are exchanged so that
+    every rank ends with the whole merged cloud in ascending (kz, ky, kx) order, exactly what the
+    single-GPU ``voxel_merge_dev`` returns.  Returns (voxels in ``out``, voxels of this rank's slab).
+    Without ``gather`` each rank keeps its slab at the start of ``out`` (a z-range of the grid per GPU).
+    """
+    splits, _ = ctx.voxel_slab_plan_dev(records_ptr, n, leaf_mm, world, cuda_stream)
+    if not gather or world == 1:
+        mine = ctx.voxel_merge_slab_dev(records_ptr, n, leaf_mm, splits[rank], splits[rank + 1], out.data_ptr(),
+                                        cuda_stream)
+        return mine, mine
+    # the slab goes to scratch first: its place in `out` depends on the lower slabs' voxel counts
+    scratch = torch.empty_like(out)
+    mine = ctx.voxel_merge_slab_dev(records_ptr, n, leaf_mm, splits[rank], splits[rank + 1], scratch.data_ptr(),
+                                    cuda_stream)
+    counts = torch.zeros(world, dtype=torch.int64, device=out.device)
+    dist.all_gather_into_tensor(counts, torch.tensor([mine], dtype=torch.int64, device=out.device), group=group)
+    counts = [int(c) for c in counts.tolist()]
+    start = 0
+    for r in range(world):
+        if counts[r]:
+            dst = out[start * 5:(start + counts[r]) * 5]
+            if r == rank:
+                dst.copy_(scratch[:mine * 5])
+            dist.broadcast(dst, src=r, group=group)
+        start += counts[r]
+    return start, mine

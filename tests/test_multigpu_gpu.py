@@ -78,6 +78,13 @@ def _worker(rank, world, port, cams_total, out_dir):
     bq.run(cs)
     fset.barrier()
     torch.cuda.synchronize()
+    # sharded voxel merge of the pulled cloud: one z-slab per rank, then exchanged
+    n_pts = layout.total_bytes // 10
+    vox = torch.zeros(n_pts * 5, dtype=torch.int16, device=dev)
+    nv, mine = multigpu.sharded_voxel_merge(ctx, pulled[0].payload.data_ptr(), n_pts, 10, rank, world, vox, cs)
+    torch.cuda.synchronize()
+    assert 0 < mine < nv
+    np.save(os.path.join(out_dir, "vox_r%d.npy" % rank), vox[: nv * 5].cpu().numpy().reshape(-1, 5))
     for f in range(n_frames):
         np.save(os.path.join(out_dir, "pull_r%d_f%d.npy" % (rank, f)), pulled[f].wire_bytes().cpu().numpy())
         np.save(os.path.join(out_dir, "fused_r%d_f%d.npy" % (rank, f)), sset.frames[f].wire_bytes().cpu().numpy())
@@ -101,3 +108,7 @@ def test_pull_fused_and_nccl_exchange_match_oracle(tmp_path, cams_total):
             for kind in ("pull", "fused", "nccl"):
                 got = np.load(os.path.join(str(tmp_path), "%s_r%d_f%d.npy" % (kind, r, f)))
                 assert np.array_equal(got, want), (kind, r, f)
+        if f == 0:
+            want_vox = R.voxel_merge(want[4:].view(np.int16).reshape(-1, 5), 10)
+            for r in range(world):
+                assert np.array_equal(np.load(os.path.join(str(tmp_path), "vox_r%d.npy" % r)), want_vox), r

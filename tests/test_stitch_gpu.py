@@ -170,6 +170,37 @@ def test_voxel_merge_skewed_and_unaligned(vctx, R):
     assert nv == len(want) and np.array_equal(out[: nv * 5].cpu().numpy().reshape(-1, 5), want)
 
 
+@pytest.mark.parametrize("n_slabs", [1, 3, 8])
+def test_voxel_slabs_concatenate_to_the_full_merge(ctx, R, n_slabs):
+    """Sharded merge: equal-population z-slabs, merged independently, concatenated in slab order,
+    are bit for bit the full merge (the multi-GPU path runs one slab per rank)."""
+    rng = np.random.default_rng(15)
+    for n, leaf, skew in [(200000, 10, False), (150001, 7, True), (5000, 1, False), (3, 10, False)]:
+        rec = random_records(rng, n)
+        rec[:, :3] = (rng.normal(0, 800, (n, 3))).clip(-32768, 32767).astype(np.int16)
+        if skew:
+            rec[rng.random(n) < 0.5, :3] = (5, 5, -1234)      # one voxel holds half the cloud
+        want = R.voxel_merge(rec, leaf)
+        d = torch.from_numpy(rec.reshape(-1)).cuda()
+        out = torch.zeros(n * 5, dtype=torch.int16, device="cuda")
+        cs = torch.cuda.current_stream().cuda_stream
+        splits, pts = ctx.voxel_slab_plan_dev(d.data_ptr(), n, leaf, n_slabs, cs)
+        assert len(splits) == n_slabs + 1 and sum(pts) == n and all(a <= b for a, b in zip(splits, splits[1:]))
+        kz = np.floor_divide(rec[:, 2].astype(np.int32), leaf)
+        assert splits[0] == kz.min() and splits[-1] == kz.max() + 1
+        got = []
+        for r in range(n_slabs):
+            assert pts[r] == int(((kz >= splits[r]) & (kz < splits[r + 1])).sum())
+            nv = ctx.voxel_merge_slab_dev(d.data_ptr(), n, leaf, splits[r], splits[r + 1], out.data_ptr(), cs)
+            torch.cuda.synchronize()
+            got.append(out[: nv * 5].cpu().numpy().reshape(-1, 5).copy())
+        assert np.array_equal(np.concatenate(got), want), (n, leaf, n_slabs)
+        if not skew and n > 1000:
+            assert max(pts) < 2.0 * n / n_slabs + 0.02 * n     # cuts are on whole planes, so only roughly equal
+    # a slab with nothing in it
+    assert ctx.voxel_merge_slab_dev(d.data_ptr(), n, 10, 3000, 3100, out.data_ptr(), cs) == 0
+
+
 def test_voxel_merge_wide_keys_fall_back(vctx, R):
     """leaf 1 mm: 3 x 16 key bits + 18 index bits do not fit the one-sweep sort word."""
     rng = np.random.default_rng(14)

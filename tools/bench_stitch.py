@@ -87,6 +87,21 @@ def main():
         ms = timed(vox, max(3, a.iters // 4))
         res[name] = {"ms": ms, "mpoints_s_in": total / ms / 1e3, "voxels": nv[0]}
         vctx.close()
+    # sharded merge (one z-slab per GPU): what each of 8 ranks would run on the same stitched cloud
+    if a.only_voxel_variant < 0:
+        vctx = pcs.Context(device=0, max_streams=1)
+        ms = timed(lambda: vctx.voxel_slab_plan_dev(st.data_ptr() + 16, total, 10, 8, cs), 5)
+        splits, pts = vctx.voxel_slab_plan_dev(st.data_ptr() + 16, total, 10, 8, cs)
+        res["voxel_slab_plan_8"] = {"ms": ms, "slab_points": pts}
+        slab_ms, slab_nv = [], []
+        for r in range(8):
+            def one():
+                nv[0] = vctx.voxel_merge_slab_dev(st.data_ptr() + 16, total, 10, splits[r], splits[r + 1], out.data_ptr(), cs)
+            slab_ms.append(timed(one, 5))
+            slab_nv.append(nv[0])
+        res["voxel_slab_merge_1of8"] = {"ms_each": slab_ms, "ms_max": max(slab_ms), "voxels": slab_nv,
+                                        "mpoints_s_if_8_gpus": total / (ms + max(slab_ms)) / 1e3}
+        vctx.close()
     if not a.skip_stitch:
         # K1a: the reference seam itself (vertices + tex coords in), 8 frames of 1280x720 per call
         nf = 8
