@@ -301,7 +301,8 @@ int pcs_b200_create(const pcs_config *cfg, pcs_ctx **out) {
             return fail(nullptr, PCS_ERR_CUDA, "cudaStreamCreate failed");
         }
     int rc = pipe_configure(ctx->device);
-    if (rc == PCS_OK && (sweep_configure<8, 256, 16>() != 0 || sweep_configure<10, 256, 16>() != 0)) rc = PCS_ERR_CUDA;
+    if (rc == PCS_OK && (sweep_configure<8, 256, 16>() != 0 || sweep_configure<10, 256, 16>() != 0))
+        rc = PCS_ERR_CUDA;
     if (rc != PCS_OK) {
         pcs_b200_destroy(ctx);
         return fail(nullptr, PCS_ERR_CUDA, "kernel attribute setup failed: %s",

@@ -310,174 +310,98 @@ sw_hist_scan(uint32_t *__restrict__ ghist) {
 template <int BITS, int THREADS, int ITEMS>
 struct SweepPassCfg {
     static constexpr int BINS = 1 << BITS, WARPS = THREADS / 32, TILE = THREADS * ITEMS, DPT = BINS / THREADS;
-    static constexpr size_t SMEM = (size_t)TILE * 8 + (size_t)(WARPS + 3) * BINS * 4;
+    static constexpr size_t SMEM = (size_t)TILE * 16 + (size_t)(WARPS + 2) * BINS * 4;     // raw + ordered tile, counters
     static_assert(DPT >= 1 && DPT * THREADS == BINS, "every thread owns BINS / THREADS digits");
 };
 
-// Decoupled look-back for 32 digits at a time, one warp: lane = (group g = lane / 8, quad q = lane % 8)
-// reads the status words of digits dq..dq+3 (dq = first digit + 4q) of predecessors
-// wstart - (g*M + m), m < M, as 16-byte volatile loads -- a window of 4*M predecessor tiles per step,
-// each tile's 32 status words one coalesced 128-byte row.  The window is folded nearest-first:
-// counts add up until a tile that carries its full prefix; an unpublished word in front of that
-// sends the whole warp back to poll the same window.  A thread-per-digit walk (one predecessor per
-// L2 round trip) made the first wave of CTAs, which all start together, wait ~R/2 round trips.
-template <int M>
-__device__ __forceinline__ void sw_lookback(const uint32_t *status, int bins, uint32_t tile, int floor_tile, int dq,
-                                            uint32_t (&before)[4], uint32_t *err) {
-    const int lane = threadIdx.x & 31, grp = lane >> 3;
-    uint32_t sum[4] = {0, 0, 0, 0};
-    uint32_t done = 0;                   // bit i: digit dq+i has reached a full prefix
-    int wstart = (int)tile - 1;          // nearest predecessor of the current window
-    int spins = 0;
-    while (true) {
-        uint4 s[M];
-#pragma unroll
-        for (int m = 0; m < M; ++m) {
-            const int t = wstart - (grp * M + m);
-            s[m] = t >= floor_tile ? ld_volatile_v4(status + (size_t)t * bins + dq)
-                          : make_uint4(SW_PREFIX, SW_PREFIX, SW_PREFIX, SW_PREFIX);   // below the floor: nothing
-        }
-        uint32_t wsum[4] = {0, 0, 0, 0}, wdone = 0, winv = 0;
-#pragma unroll
-        for (int m = 0; m < M; ++m) {
-            const uint32_t e[4] = {s[m].x, s[m].y, s[m].z, s[m].w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t f = e[i] >> 30;
-                if (!(((wdone | winv) >> i) & 1u)) {
-                    if (f == 0) {
-                        winv |= 1u << i;
-                    } else {
-                        wsum[i] += e[i] & SW_VALUE;
-                        if (f == 2) wdone |= 1u << i;
-                    }
-                }
-            }
-        }
-        // ordered fold across the four lane groups (the lower group holds the nearer tiles)
-#pragma unroll
-        for (int step = 8; step <= 16; step <<= 1) {
-            const uint32_t mine = wdone | (winv << 4);
-            const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, step);
-            const bool lower = (lane & step) == 0;
-            const uint32_t af = lower ? mine : other, bf = lower ? other : mine;
-            uint32_t nd = 0, ni = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t o = __shfl_xor_sync(0xffffffffu, wsum[i], step);
-                const uint32_t as = lower ? wsum[i] : o, bs = lower ? o : wsum[i];
-                const bool a_closed = ((af >> i) | (af >> (4 + i))) & 1u;
-                wsum[i] = a_closed ? as : as + bs;
-                const uint32_t src = a_closed ? af : bf;
-                nd |= ((src >> i) & 1u) << i;
-                ni |= ((src >> (4 + i)) & 1u) << i;
-            }
-            wdone = nd;
-            winv = ni;
-        }
-        if (__any_sync(0xffffffffu, (winv & ~done) != 0)) {
-            if (++spins >= SW_SPIN_LIMIT) {
-                if (lane == 0) atomicExch(err, 1u);
-                break;
-            }
-            continue;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (!((done >> i) & 1u)) sum[i] += wsum[i];
-        done |= wdone;
-        if (__all_sync(0xffffffffu, done == 0xFu)) break;
-        wstart -= 4 * M;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) before[i] = sum[i];
-}
-
-// Sum of the counts the earlier tiles of this tile's group published for 32 digits (same lane layout
-// as sw_lookback with M = 4: one step covers the whole group).  Tile words only ever carry counts.
-__device__ __forceinline__ void sw_group_sum(const uint32_t *status, int bins, uint32_t tile, int floor_tile, int dq,
-                                             uint32_t (&sum)[4], uint32_t *err) {
-    const int lane = threadIdx.x & 31, grp = lane >> 3;
-    int spins = 0;
-    while (true) {
-        uint32_t acc[4] = {0, 0, 0, 0};
-        bool ready = true;
-#pragma unroll
-        for (int m = 0; m < SW_GROUP / 4; ++m) {
-            const int t = (int)tile - 1 - (grp * (SW_GROUP / 4) + m);
-            if (t >= floor_tile) {
-                const uint4 v = ld_volatile_v4(status + (size_t)t * bins + dq);
-                ready = ready && (v.x >> 30) && (v.y >> 30) && (v.z >> 30) && (v.w >> 30);
-                acc[0] += v.x & SW_VALUE; acc[1] += v.y & SW_VALUE; acc[2] += v.z & SW_VALUE; acc[3] += v.w & SW_VALUE;
-            }
-        }
-        if (__all_sync(0xffffffffu, ready)) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-                acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
-                sum[i] = acc[i];
-            }
-            return;
-        }
-        if (++spins >= SW_SPIN_LIMIT) {
-            if (lane == 0) atomicExch(err, 1u);
-            return;
-        }
-    }
-}
-
-template <int BITS, int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS, (BITS <= 8 ? 3 : 2))
+// Decoupled look-back, two levels.  Every tile publishes its digit counts (tile words).  The last
+// tile of each group of SW_GROUP has to add up the 15 tiles before it anyway: that sum plus its own
+// counts is the group's total, which it publishes as a group word, followed by the group's inclusive
+// prefix once it knows what lies before the group.  A tile's digits-before = the earlier tiles of
+// its own group + a walk over group words, 16 tiles per word: with ~450 tiles in flight a one-level
+// walk was most of the kernel.  One thread per digit, a step's loads issued together.
+template <int BITS, int THREADS, int ITEMS, bool BALLOT>
+__global__ void __launch_bounds__(THREADS, (BITS > 8 || THREADS > 256 ? 2 : (ITEMS <= 8 ? 4 : 3)))
 sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n, int shift,
-        const uint32_t *__restrict__ gbase, uint32_t *status, uint32_t *gstatus, uint32_t *gacc, uint32_t *gdone,
-        int n_tiles, uint32_t *ticket, uint32_t *err) {
+        const uint32_t *__restrict__ gbase, uint32_t *status, uint32_t *gstatus,
+        int n_tiles, uint32_t *ticket, uint32_t *err, int probe) {
     using Cfg = SweepPassCfg<BITS, THREADS, ITEMS>;
     constexpr int BINS = Cfg::BINS, WARPS = Cfg::WARPS, TILE = Cfg::TILE, DPT = Cfg::DPT;
     extern __shared__ __align__(16) uint8_t sw_smem[];
     uint64_t *skeys = reinterpret_cast<uint64_t *>(sw_smem);     // [TILE] the tile in digit order
-    uint32_t *wh = reinterpret_cast<uint32_t *>(skeys + TILE);   // [WARPS][BINS] per-warp digit counters
+    uint64_t *raw = skeys + TILE;                                 // [TILE] the tile as it lies in `in`
+    uint32_t *wh = reinterpret_cast<uint32_t *>(raw + TILE);     // [WARPS][BINS] per-warp digit counters
     uint32_t *tile_excl = wh + WARPS * BINS;                      // [BINS] first tile-local slot of a digit
-    uint32_t *tile_cnt = tile_excl + BINS;                        // [BINS] elements of a digit in this tile
-    uint32_t *gdelta = tile_cnt + BINS;                           // [BINS] global slot = gdelta + tile-local slot
-    __shared__ uint32_t s_tile, s_closer, warp_tot[33];
+    uint32_t *gdelta = tile_excl + BINS;                          // [BINS] global slot = gdelta + tile-local slot
+    __shared__ uint32_t s_tile, s_bulk, warp_tot[33];
+    __shared__ __align__(8) uint64_t s_bar;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);   // tiles are taken in the order CTAs start running
+    // The tile is one contiguous span of `in`: a single bulk copy (TMA) brings it to shared memory while
+    // the counters are cleared.  (Sixteen register loads per thread were sunk by ptxas next to their
+    // uses to hold the register budget -- twelve exposed DRAM round trips per tile.)
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&s_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t t = atomicAdd(ticket, 1u);   // tiles are taken in the order CTAs start running
+        s_tile = t;
+        const long long first = (long long)t * TILE;
+        const uint32_t bytes = (uint32_t)min((long long)TILE, (long long)n - first) * 8u;
+        const bool bulk = (bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(in + first)) & 15) == 0;
+        s_bulk = bulk ? 1u : 0u;
+        if (bulk) {
+            mbar_expect_tx(smem_u32(&s_bar), bytes);
+            bulk_load(smem_u32(raw), in + first, bytes, smem_u32(&s_bar));
+        }
+    }
     for (int k = threadIdx.x; k < WARPS * BINS; k += THREADS) wh[k] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t group = tile / SW_GROUP;
     const int group_first = (int)(group * SW_GROUP);
-    const uint32_t group_tiles = (uint32_t)min(SW_GROUP, n_tiles - group_first);
     const int tbase = (int)tile * TILE;
     const int wbase = tbase + warp * (32 * ITEMS);   // warp-blocked: warp w owns 32*ITEMS consecutive words
+    const uint64_t *wraw = raw + warp * (32 * ITEMS) + lane;
     uint32_t *mywh = wh + warp * BINS;
-    uint64_t key[ITEMS];
     uint32_t local[ITEMS];
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const int i = wbase + k * 32 + lane;
-        key[k] = i < n ? in[i] : ~0ull;
+    if (s_bulk) {
+        mbar_wait(smem_u32(&s_bar), 0);
+    } else {      // ragged last tile
+        for (int j = threadIdx.x; j < TILE; j += THREADS)
+            if (tbase + j < n) raw[j] = in[tbase + j];
+        __syncthreads();
     }
+    // lanes holding the same digit, from one ballot per digit bit (MATCH.ANY is no faster and occupies
+    // a per-SM unit for ~35 cycles per warp instruction).  All masks first -- the ballots of different
+    // items are independent -- then the serial walk over the warp's counters.
+    uint32_t mask[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const bool valid = wbase + k * 32 + lane < n;
-        const uint32_t d = (uint32_t)(key[k] >> shift) & (BINS - 1);
-        // lanes holding the same digit, from one ballot per digit bit: MATCH.ANY measured ~35 cycles of
-        // a per-SM unit per warp instruction (a 57 us floor per pass on 14.7 M words), BITS ballots do not
-        uint32_t mask = __ballot_sync(0xffffffffu, valid);
+        const uint32_t d = (uint32_t)(wraw[k * 32] >> shift) & (BINS - 1);
+        if (BALLOT) {
+            uint32_t m = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
-        for (int b = 0; b < BITS; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const uint32_t v = __ballot_sync(0xffffffffu, bit);
-            mask &= bit ? v : ~v;
+            for (int b = 0; b < BITS; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const uint32_t v = __ballot_sync(0xffffffffu, bit);
+                m &= bit ? v : ~v;
+            }
+            mask[k] = m;
+        } else {
+            mask[k] = __match_any_sync(0xffffffffu, valid ? d : (uint32_t)(BINS + lane));
         }
-        const int leader = __ffs(mask) - 1;
-        const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (probe & 4) { local[k] = 0; continue; }
+        const bool valid = wbase + k * 32 + lane < n;
+        const uint32_t d = (uint32_t)(wraw[k * 32] >> shift) & (BINS - 1);
+        const int leader = __ffs(mask[k]) - 1;
+        const uint32_t rank = __popc(mask[k] & ((1u << lane) - 1u));
         uint32_t prev = 0;
         if (valid && lane == leader) {
             prev = mywh[d];
-            mywh[d] = prev + __popc(mask);
+            mywh[d] = prev + __popc(mask[k]);
         }
         __syncwarp();
         prev = __shfl_sync(0xffffffffu, prev, leader);
@@ -498,10 +422,8 @@ sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n, int 
         }
         cnt[j] = run;
         tsum += run;
-        tile_cnt[d] = run;
-        // let the successors see this tile's counts as early as possible, and add them to the group's
+        // let the successors see this tile's counts as early as possible
         st_volatile_u32(status + (size_t)tile * BINS + d, SW_AGG | run);
-        if (run) atomicAdd(gacc + (size_t)group * BINS + d, run);
     }
     uint32_t total;
     uint32_t ex = block_exclusive_scan(tsum, warp_tot, total);
@@ -516,55 +438,91 @@ sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n, int 
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         if (wbase + k * 32 + lane < n) {
-            const uint32_t d = (uint32_t)(key[k] >> shift) & (BINS - 1);
-            skeys[tile_excl[d] + mywh[d] + local[k]] = key[k];
+            const uint64_t key = wraw[k * 32];
+            const uint32_t d = (uint32_t)(key >> shift) & (BINS - 1);
+            skeys[tile_excl[d] + mywh[d] + local[k]] = key;
         }
     }
-    // The tile that completes its group publishes the group's totals (tile_cnt becomes the group's):
-    // the group-level status words are what later tiles walk over, 16 tiles per word.
-    // (every thread's counts and group sums happen-before the barrier above; one cumulative fence
-    // then orders them before this tile is counted as done)
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_closer = (atomicAdd(gdone + group, 1u) + 1u == group_tiles) ? 1u : 0u;
-    }
-    __syncthreads();
-    const bool closer = s_closer != 0;
-    if (closer) {
-        __threadfence();
+    // The LAST tile of a group speaks for the group: what it finds before itself inside the group plus
+    // its own counts are the group's totals (published as soon as known), and once it knows what lies
+    // before the group, the group's inclusive prefix.  No counters, no atomics.
+    const bool speaker = (int)tile == group_first + SW_GROUP - 1;
+    // digits before this tile = the group's earlier tiles + everything before the group.  One thread
+    // per digit; the loads of a step are issued together (one L2 round trip per step, not per word):
+    // all <= 15 tile words of the group at once, then the group words 8 at a time, nearest first,
+    // until one carries a full prefix.  A row of words is one coalesced line per warp.
+    const int n_before = (int)tile - group_first;
+    constexpr int GB = 16;      // group words per step
 #pragma unroll
-        for (int j = 0; j < DPT; ++j) {
-            const int d = threadIdx.x * DPT + j;
-            const uint32_t tot = ld_volatile_u32(gacc + (size_t)group * BINS + d);
-            tile_cnt[d] = tot;
-            st_volatile_u32(gstatus + (size_t)group * BINS + d, (group == 0 ? SW_PREFIX : SW_AGG) | tot);
-        }
-        __syncthreads();
-    }
-    // digits before this tile = the group's earlier tiles (one window, it stops at the group's first
-    // tile) + everything before the group (a walk over group words: 16 groups = 256 tiles per step)
-    for (int g32 = warp; g32 < BINS / 32; g32 += WARPS) {
-        const int dq = g32 * 32 + 4 * (lane & 7);
-        uint32_t in_group[4] = {0, 0, 0, 0}, before_group[4] = {0, 0, 0, 0};
-        if ((int)tile > group_first) sw_group_sum(status, BINS, tile, group_first, dq, in_group, err);
-        if (group > 0) sw_lookback<4>(gstatus, BINS, group, 0, dq, before_group, err);
-        if (lane < 8) {
-            uint32_t pub[4];
+    for (int j = 0; j < DPT; ++j) {
+        const int d = threadIdx.x * DPT + j;
+        uint32_t in_group = 0, before_group = 0;
+        bool need_tiles = n_before > 0 && !(probe & 1), need_groups = group > 0 && !(probe & 1);
+        int gs = (int)group - 1;
+        for (int spins = 0; need_tiles || need_groups;) {
+            uint32_t tv[SW_GROUP - 1], gv[GB];
+            if (need_tiles) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                gdelta[dq + i] = gbase[dq + i] + before_group[i] + in_group[i] - tile_excl[dq + i];
-                pub[i] = SW_PREFIX | ((before_group[i] + tile_cnt[dq + i]) & SW_VALUE);
+                for (int t = 0; t < SW_GROUP - 1; ++t)
+                    tv[t] = t < n_before ? ld_volatile_u32(status + (size_t)((int)tile - 1 - t) * BINS + d) : SW_AGG;
             }
-            if (closer && group > 0)
-                st_volatile_v4(gstatus + (size_t)group * BINS + dq, make_uint4(pub[0], pub[1], pub[2], pub[3]));
+            if (need_groups) {
+#pragma unroll
+                for (int t = 0; t < GB; ++t)
+                    gv[t] = gs - t >= 0 ? ld_volatile_u32(gstatus + (size_t)(gs - t) * BINS + d) : SW_PREFIX;
+            }
+            bool progress = false;
+            if (need_tiles) {
+                uint32_t acc = 0, flags = 0xFFFFFFFFu;
+#pragma unroll
+                for (int t = 0; t < SW_GROUP - 1; ++t) {
+                    acc += tv[t] & SW_VALUE;
+                    flags &= tv[t];
+                }
+                if (flags & SW_AGG) {      // every tile word carries SW_AGG once published
+                    in_group = acc;
+                    need_tiles = false;
+                    progress = true;
+                    if (speaker)
+                        st_volatile_u32(gstatus + (size_t)group * BINS + d,
+                                        (group == 0 ? SW_PREFIX : SW_AGG) | (in_group + cnt[j]));
+                }
+            }
+            if (need_groups) {
+                uint32_t acc = 0;
+                bool ready = true, found = false;
+#pragma unroll
+                for (int t = 0; t < GB; ++t) {
+                    if (!found) {
+                        const uint32_t f = gv[t] >> 30;
+                        if (f == 0) ready = false;
+                        acc += gv[t] & SW_VALUE;
+                        if (f == 2) found = true;
+                    }
+                }
+                if (ready) {     // else: an unpublished group in front of the first full prefix, poll again
+                    before_group += acc;
+                    gs -= GB;
+                    if (found) need_groups = false;
+                    progress = true;
+                }
+            }
+            if (!progress) {
+                if (++spins >= SW_SPIN_LIMIT) { atomicExch(err, 1u); break; }
+                __nanosleep(64);      // polling in a tight loop starves the tiles being waited for
+            }
         }
+        gdelta[d] = gbase[d] + before_group + in_group - tile_excl[d];
+        if (speaker && group > 0)
+            st_volatile_u32(gstatus + (size_t)group * BINS + d, SW_PREFIX | ((before_group + in_group + cnt[j]) & SW_VALUE));
     }
     __syncthreads();
     const int nvalid = min(TILE, n - tbase);
     for (int j = threadIdx.x; j < nvalid; j += THREADS) {
         const uint64_t k = skeys[j];
         const uint32_t d = (uint32_t)(k >> shift) & (BINS - 1);
-        out[gdelta[d] + (uint32_t)j] = k;
+        if (!(probe & 2)) out[gdelta[d] + (uint32_t)j] = k;
+        else if (k == 0x123456789abcdefull) out[j] = k;
     }
 }
 
@@ -891,7 +849,9 @@ inline int sweep_zbins(const SweepGeom &g) { return (32767 + g.bias) / g.leaf + 
 template <int BITS, int THREADS, int ITEMS>
 inline int sweep_configure() {
     using Cfg = SweepPassCfg<BITS, THREADS, ITEMS>;
-    if (cudaFuncSetAttribute(sw_pass<BITS, THREADS, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(sw_pass<BITS, THREADS, ITEMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)Cfg::SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(sw_pass<BITS, THREADS, ITEMS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)Cfg::SMEM) != cudaSuccess) return -2;
     return 0;
 }
@@ -966,8 +926,8 @@ inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int lea
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     // sized for the worst case (every point inside, full-range keys) so that nothing is allocated
     // between the two phases:
-    // [bounds][words0][words1][pay] | zeroed: [ghist][tickets][err][slot counter][group status, sums,
-    // done counters][status][slots] |
+    // [bounds][words0][words1][pay] | zeroed: [ghist][tickets][err][slot counter][group
+    // words][status][slots] |
     // [info][chunk_off][ownerpos][slotkey][nv]
     const int passes_max = (3 * sweep_bits_for(zbins) + BITS - 1) / BITS;
     const int tiles_max = (n + Cfg::TILE - 1) / Cfg::TILE, chunks_max = (n + SW_CHUNK - 1) / SW_CHUNK;
@@ -976,9 +936,7 @@ inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int lea
                  o_zero = o_pay + al((size_t)n * 8),
                  o_ghist = o_zero, o_ticket = o_ghist + al((size_t)passes_max * BINS * 4), o_err = o_ticket + al(64),
                  o_cnt = o_err + al(64), o_gstat = o_cnt + al(64),
-                 o_gacc = o_gstat + al((size_t)passes_max * groups_max * BINS * 4),
-                 o_gdone = o_gacc + al((size_t)passes_max * groups_max * BINS * 4),
-                 o_status = o_gdone + al((size_t)passes_max * groups_max * 4),
+                 o_status = o_gstat + al((size_t)passes_max * groups_max * BINS * 4),
                  o_slots = o_status + al((size_t)passes_max * tiles_max * BINS * 4),
                  o_zero_end = o_slots + al((size_t)chunks_max * 32),
                  o_info = o_zero_end, o_off = o_info + al((size_t)chunks_max * 8), o_owner = o_off + al((size_t)chunks_max * 4),
@@ -1016,8 +974,7 @@ inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int lea
     uint32_t *ghist = (uint32_t *)(s.buf + o_ghist), *ticket = (uint32_t *)(s.buf + o_ticket),
              *err = (uint32_t *)(s.buf + o_err), *slot_counter = (uint32_t *)(s.buf + o_cnt),
              *status = (uint32_t *)(s.buf + o_status), *slots = (uint32_t *)(s.buf + o_slots),
-             *gstatus = (uint32_t *)(s.buf + o_gstat), *gacc = (uint32_t *)(s.buf + o_gacc),
-             *gdone = (uint32_t *)(s.buf + o_gdone),
+             *gstatus = (uint32_t *)(s.buf + o_gstat),
              *chunk_off = (uint32_t *)(s.buf + o_off), *ownerpos = (uint32_t *)(s.buf + o_owner);
     uint64_t *info = (uint64_t *)(s.buf + o_info), *slotkey = (uint64_t *)(s.buf + o_skey);
     int32_t *nv_dev = (int32_t *)(s.buf + o_nv);
@@ -1030,11 +987,13 @@ inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int lea
     else
         sw_keys_hist<BITS, false><<<kh_grid, SW_KH_THREADS, (size_t)passes * BINS * 4, cs>>>(rec, n, g, passes, w0, pay, ghist, slot_counter);
     sw_hist_scan<BITS><<<passes, BINS, 0, cs>>>(ghist);
+    static const bool ballot = pipe_knob("PCS_SW_BALLOT", 1, 0, 1) != 0;     // 0: MATCH.ANY ranking (tuning knob)
+    static const int probe = pipe_knob("PCS_SW_PROBE", 0, 0, 15);            // timing probes (wrong results!)
     for (int p = 0; p < passes; ++p) {
-        sw_pass<BITS, THREADS, ITEMS><<<n_tiles, THREADS, Cfg::SMEM, cs>>>(
+        auto kern = ballot ? sw_pass<BITS, THREADS, ITEMS, true> : sw_pass<BITS, THREADS, ITEMS, false>;
+        kern<<<n_tiles, THREADS, Cfg::SMEM, cs>>>(
             w0, w1, m, g.idx_bits + p * BITS, ghist + (size_t)p * BINS, status + (size_t)p * n_tiles * BINS,
-            gstatus + (size_t)p * groups_max * BINS, gacc + (size_t)p * groups_max * BINS,
-            gdone + (size_t)p * groups_max, n_tiles, ticket + p, err);
+            gstatus + (size_t)p * groups_max * BINS, n_tiles, ticket + p, err, probe);
         std::swap(w0, w1);
     }
     const int cblocks = (n_chunks + 7) / 8;
