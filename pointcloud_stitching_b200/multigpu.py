@@ -224,8 +224,11 @@ def sharded_voxel_merge(ctx, records_ptr, n, leaf_mm, rank, world, out, cuda_str
     single-GPU ``voxel_merge_dev`` returns.  Returns (voxels in ``out``, voxels of this rank's slab).
     Without ``gather`` each rank keeps its slab at the start of ``out`` (a z-range of the grid per GPU).
     """
+    if world == 1:
+        mine = ctx.voxel_merge_dev(records_ptr, n, leaf_mm, out.data_ptr(), cuda_stream)
+        return mine, mine
     splits, _ = ctx.voxel_slab_plan_dev(records_ptr, n, leaf_mm, world, cuda_stream)
-    if not gather or world == 1:
+    if not gather:
         mine = ctx.voxel_merge_slab_dev(records_ptr, n, leaf_mm, splits[rank], splits[rank + 1], out.data_ptr(),
                                         cuda_stream)
         return mine, mine
@@ -242,6 +245,6 @@ def sharded_voxel_merge(ctx, records_ptr, n, leaf_mm, rank, world, out, cuda_str
             dst = out[start * 5:(start + counts[r]) * 5]
             if r == rank:
                 dst.copy_(scratch[:mine * 5])
-            dist.broadcast(dst, src=r, group=group)
+            dist.broadcast(dst.view(torch.uint8), src=r, group=group)     # NCCL has no int16
         start += counts[r]
     return start, mine
