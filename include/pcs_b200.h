@@ -221,6 +221,15 @@ PCS_API int pcs_b200_voxel_slab_plan_dev(pcs_ctx *ctx, const int16_t *records_de
 PCS_API int pcs_b200_voxel_merge_slab_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
                                   int kz_lo, int kz_hi, int16_t *out_dev, void *cuda_stream);
 
+/* PLY dump of the stitched pcl::PointXYZRGB cloud (the 32-byte records pcs_b200_stitch_pcl_dev writes
+ * to cloud32_dev), replacing pcl::io::savePLYFileBinary in visualize()
+ * (src/pcs-multicamera-client.cpp:482-489).  _rows_dev: n 15-byte binary PLY vertices
+ * (float x, y, z; uchar red, green, blue) into rows_dev.  save_ply: header + vertices + PCL's
+ * one-row camera element into a file.  Both return n. */
+PCS_API int pcs_b200_cloud_to_ply_rows_dev(pcs_ctx *ctx, const void *cloud32_dev, int n, uint8_t *rows_dev,
+                                   void *cuda_stream);
+PCS_API int pcs_b200_save_ply(pcs_ctx *ctx, const void *cloud32_dev, int n, const char *path);
+
 /* Blocks until everything issued on cuda_stream by this context has finished. */
 PCS_API int pcs_b200_synchronize(pcs_ctx *ctx, void *cuda_stream);
 

@@ -129,6 +129,8 @@ def _load():
         "pcs_b200_voxel_merge": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
         "pcs_b200_voxel_slab_plan_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, i32p, i32p, vp]),
         "pcs_b200_voxel_merge_slab_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+        "pcs_b200_cloud_to_ply_rows_dev": (C.c_int, [vp, vp, C.c_int, vp, vp]),
+        "pcs_b200_save_ply": (C.c_int, [vp, vp, C.c_int, C.c_char_p]),
         "pcs_b200_synchronize": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -331,6 +333,13 @@ class Context:
     def voxel_merge_slab_dev(self, records_ptr, n, leaf_mm, kz_lo, kz_hi, out_ptr, cuda_stream=0):
         return self._check(lib.pcs_b200_voxel_merge_slab_dev(self.handle, records_ptr, n, leaf_mm, kz_lo, kz_hi,
                                                              out_ptr, cuda_stream))
+
+    def cloud_to_ply_rows_dev(self, cloud32_ptr, n, rows_ptr, cuda_stream=0):
+        return self._check(lib.pcs_b200_cloud_to_ply_rows_dev(self.handle, cloud32_ptr, n, rows_ptr, cuda_stream))
+
+    def save_ply(self, cloud32_ptr, n, path):
+        """pcl::io::savePLYFileBinary of the stitched cloud (32-byte PCL points on the device)."""
+        return self._check(lib.pcs_b200_save_ply(self.handle, cloud32_ptr, n, os.fsencode(path)))
 
     def synchronize(self, cuda_stream=0):
         self._check(lib.pcs_b200_synchronize(self.handle, cuda_stream))

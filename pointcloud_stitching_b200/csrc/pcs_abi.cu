@@ -922,4 +922,64 @@ int pcs_b200_voxel_merge(pcs_ctx *ctx, const int16_t *records_host, int n, int l
     return rc;
 }
 
+// ---- PLY dump ----------------------------------------------------------------------------
+int pcs_b200_cloud_to_ply_rows_dev(pcs_ctx *ctx, const void *cloud32_dev, int n, uint8_t *rows_dev, void *cuda_stream) {
+    if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
+    if (n < 0 || (n && (!cloud32_dev || !rows_dev))) return fail(ctx, PCS_ERR_INVALID, "bad PLY arguments");
+    if (reinterpret_cast<uintptr_t>(cloud32_dev) & 15) return fail(ctx, PCS_ERR_INVALID, "cloud must be 16-byte aligned");
+    if (n == 0) return 0;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int groups = (n + 31) / 32;
+    const int grid = std::max(1, std::min((groups + PLY_THREADS / 32 - 1) / (PLY_THREADS / 32), ctx->sm_count * 8));
+    ply_rows<<<grid, PLY_THREADS, 0, (cudaStream_t)cuda_stream>>>(reinterpret_cast<const uint4 *>(cloud32_dev), n, rows_dev);
+    CU(ctx, cudaGetLastError());
+    return n;
+}
+
+// Header as PCL's PLYWriter emits it for a PointXYZRGB cloud (recalled from PCL 1.8; PCL is not in
+// /root/reference, so the exact text is unpinned -- any PLY reader accepts it): vertex element, then a
+// one-row camera element (identity pose, focal 0, viewport = cloud width x height = n x 1).
+int pcs_b200_save_ply(pcs_ctx *ctx, const void *cloud32_dev, int n, const char *path) {
+    if (!ctx || !path) return fail(ctx, PCS_ERR_INVALID, "null argument");
+    if (n < 0 || (n && !cloud32_dev)) return fail(ctx, PCS_ERR_INVALID, "bad PLY arguments");
+    CU(ctx, cudaSetDevice(ctx->device));
+    uint8_t *d_rows = nullptr;
+    std::vector<uint8_t> rows((size_t)n * PLY_ROW);
+    if (n) {
+        if (cudaMalloc(&d_rows, (size_t)n * PLY_ROW + 16) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, PCS_ERR_NOMEM, "cudaMalloc failed");
+        }
+        cudaStream_t cs = ctx->streams[0].cs;
+        int rc = pcs_b200_cloud_to_ply_rows_dev(ctx, cloud32_dev, n, d_rows, cs);
+        if (rc >= 0 && (cudaMemcpyAsync(rows.data(), d_rows, rows.size(), cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
+                        cudaStreamSynchronize(cs) != cudaSuccess))
+            rc = fail(ctx, PCS_ERR_CUDA, "PLY copy back failed: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(d_rows);
+        if (rc < 0) return rc;
+    }
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(ctx, PCS_ERR_INVALID, "cannot open %s", path);
+    fprintf(f, "ply\nformat binary_little_endian 1.0\ncomment PCL generated\nelement vertex %d\n"
+               "property float x\nproperty float y\nproperty float z\n"
+               "property uchar red\nproperty uchar green\nproperty uchar blue\n"
+               "element camera 1\n"
+               "property float view_px\nproperty float view_py\nproperty float view_pz\n"
+               "property float x_axisx\nproperty float x_axisy\nproperty float x_axisz\n"
+               "property float y_axisx\nproperty float y_axisy\nproperty float y_axisz\n"
+               "property float z_axisx\nproperty float z_axisy\nproperty float z_axisz\n"
+               "property float focal\nproperty float scalex\nproperty float scaley\n"
+               "property float centerx\nproperty float centery\n"
+               "property int viewportx\nproperty int viewporty\n"
+               "property float k1\nproperty float k2\nend_header\n", n);
+    bool ok = rows.empty() || fwrite(rows.data(), 1, rows.size(), f) == rows.size();
+    const float cam_a[17] = {0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0};
+    const int32_t viewport[2] = {n, 1};
+    const float k12[2] = {0, 0};
+    ok = ok && fwrite(cam_a, 4, 17, f) == 17 && fwrite(viewport, 4, 2, f) == 2 && fwrite(k12, 4, 2, f) == 2;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(ctx, PCS_ERR_INVALID, "short write to %s", path);
+    return n;
+}
+
 }  // extern "C"

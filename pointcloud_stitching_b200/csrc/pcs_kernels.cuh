@@ -462,4 +462,41 @@ stitch_vec(const __grid_constant__ CamTable tab, const __grid_constant__ TfTable
         if (k * 32 + lane < n16) st_global_v4(dst + (size_t)(k * 32 + lane) * 16, slab[k * 32 + lane]);
 }
 
+// ---- PLY vertex rows -----------------------------------------------------------------------
+// The reference's viewer path can dump the stitched pcl::PointXYZRGB cloud with
+// pcl::io::savePLYFileBinary (src/pcs-multicamera-client.cpp:482-489).  A binary PLY vertex of
+// that cloud is 15 bytes: float x, y, z + uchar red, green, blue.  One warp turns 32 of the 32-byte
+// PCL points into 480 contiguous bytes through shared memory, so both sides move 16 bytes per lane.
+constexpr int PLY_ROW = 15, PLY_THREADS = 256;
+
+__global__ void __launch_bounds__(PLY_THREADS)
+ply_rows(const uint4 *__restrict__ cloud32, int n, uint8_t *__restrict__ rows) {
+    __shared__ __align__(16) uint8_t stage[PLY_THREADS / 32][32 * PLY_ROW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_groups = (n + 31) / 32;
+    for (int grp = blockIdx.x * (PLY_THREADS / 32) + warp; grp < n_groups; grp += gridDim.x * (PLY_THREADS / 32)) {
+        const int i = grp * 32 + lane;
+        uint8_t *mine = stage[warp] + lane * PLY_ROW;
+        if (i < n) {
+            const uint4 xyzw = __ldg(cloud32 + 2 * (size_t)i);
+            const uint32_t bgra = __ldg(reinterpret_cast<const uint32_t *>(cloud32 + 2 * (size_t)i + 1));
+            const uint32_t w[3] = {xyzw.x, xyzw.y, xyzw.z};
+#pragma unroll
+            for (int k = 0; k < 12; ++k) mine[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+            mine[12] = (uint8_t)(bgra >> 16);     // PCL packs b, g, r, a
+            mine[13] = (uint8_t)(bgra >> 8);
+            mine[14] = (uint8_t)bgra;
+        }
+        __syncwarp();
+        const int valid = min(32, n - grp * 32);
+        uint8_t *dst = rows + (size_t)grp * 32 * PLY_ROW;
+        if (valid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            if (lane < 30) reinterpret_cast<uint4 *>(dst)[lane] = reinterpret_cast<const uint4 *>(stage[warp])[lane];
+        } else {
+            for (int b = lane; b < valid * PLY_ROW; b += 32) dst[b] = stage[warp][b];
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace pcs

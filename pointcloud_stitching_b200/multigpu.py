@@ -227,24 +227,27 @@ def sharded_voxel_merge(ctx, records_ptr, n, leaf_mm, rank, world, out, cuda_str
     if world == 1:
         mine = ctx.voxel_merge_dev(records_ptr, n, leaf_mm, out.data_ptr(), cuda_stream)
         return mine, mine
-    splits, _ = ctx.voxel_slab_plan_dev(records_ptr, n, leaf_mm, world, cuda_stream)
+    splits, pts = ctx.voxel_slab_plan_dev(records_ptr, n, leaf_mm, world, cuda_stream)
     if not gather:
         mine = ctx.voxel_merge_slab_dev(records_ptr, n, leaf_mm, splits[rank], splits[rank + 1], out.data_ptr(),
                                         cuda_stream)
         return mine, mine
-    # the slab goes to scratch first: its place in `out` depends on the lower slabs' voxel counts
-    scratch = torch.empty_like(out)
-    mine = ctx.voxel_merge_slab_dev(records_ptr, n, leaf_mm, splits[rank], splits[rank + 1], scratch.data_ptr(),
+    # A slab cannot produce more voxels than it has points, and the plan gives every rank all the slab
+    # populations: each rank merges into its block of a [world x cap] staging buffer, ONE all-gather
+    # moves the blocks (the first 8 bytes of a block carry its voxel count), and the slabs are then
+    # packed back to back in slab order.
+    blk = (4 + max(pts) * 5 + 7) // 8 * 8        # int16 per block: [int64 voxel count][records], 16-byte multiple
+    stage = torch.empty(world * blk, dtype=torch.int16, device=out.device)
+    block = stage[rank * blk:(rank + 1) * blk]
+    mine = ctx.voxel_merge_slab_dev(records_ptr, n, leaf_mm, splits[rank], splits[rank + 1], block[4:].data_ptr(),
                                     cuda_stream)
-    counts = torch.zeros(world, dtype=torch.int64, device=out.device)
-    dist.all_gather_into_tensor(counts, torch.tensor([mine], dtype=torch.int64, device=out.device), group=group)
-    counts = [int(c) for c in counts.tolist()]
+    block[:4].view(torch.int64)[0] = mine
+    dist.all_gather_into_tensor(stage.view(torch.uint8), block.view(torch.uint8), group=group)   # NCCL has no int16
+    counts = stage.view(world, blk)[:, :4].contiguous().view(torch.int64).reshape(-1).tolist()
     start = 0
     for r in range(world):
-        if counts[r]:
-            dst = out[start * 5:(start + counts[r]) * 5]
-            if r == rank:
-                dst.copy_(scratch[:mine * 5])
-            dist.broadcast(dst.view(torch.uint8), src=r, group=group)     # NCCL has no int16
-        start += counts[r]
+        c = int(counts[r])
+        if c:
+            out[start * 5:(start + c) * 5].copy_(stage[r * blk + 4:r * blk + 4 + c * 5])
+        start += c
     return start, mine

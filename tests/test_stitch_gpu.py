@@ -115,6 +115,48 @@ def test_device_path_and_cloud32(ctx, R):
     assert np.array_equal(st[: size + 4].cpu().numpy(), R.concat(pay, 2))
 
 
+def test_ply_dump_of_the_stitched_cloud(ctx, R, tmp_path):
+    """visualize()'s save path (src/pcs-multicamera-client.cpp:482-489): the stitched PCL cloud as a binary
+    PLY -- float x, y, z + uchar red, green, blue per vertex, in stitch order."""
+    rng = np.random.default_rng(6)
+    pay = [random_records(rng, n) for n in (40000, 8, 12345)]
+    tfs = [synth.TF_STITCH[k] for k in range(3)]
+    d = [dev(p.reshape(-1)) for p in pay]
+    total = sum(p.shape[0] for p in pay)
+    st = torch.zeros(total * 10 + 32, dtype=torch.uint8, device="cuda")
+    cloud = torch.zeros(total * 8, dtype=torch.float32, device="cuda")
+    cs = torch.cuda.current_stream().cuda_stream
+    ctx.stitch_pcl_dev([t.data_ptr() for t in d], [p.size for p in pay], 1, tfs, st.data_ptr() + 12, total * 10 + 4,
+                       cloud.data_ptr(), cs)
+    torch.cuda.synchronize()
+    want = np.concatenate([R.transform_cloud(R.unpack(p), t) for p, t in zip(pay, tfs)])
+    path = str(tmp_path / "stitched_cloud_0.ply")
+    assert ctx.save_ply(cloud.data_ptr(), total, path) == total
+    raw = open(path, "rb").read()
+    end = raw.index(b"end_header\n") + len(b"end_header\n")
+    header = raw[:end].decode().split("\n")
+    assert header[0] == "ply" and header[1] == "format binary_little_endian 1.0"
+    assert "element vertex %d" % total in header and "element camera 1" in header
+    props = [h.split()[-1] for h in header[header.index("element vertex %d" % total) + 1:header.index("element camera 1")]]
+    assert props == ["x", "y", "z", "red", "green", "blue"]
+    row = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("r", "u1"), ("g", "u1"), ("b", "u1")])
+    assert len(raw) == end + total * 15 + 21 * 4
+    got = np.frombuffer(raw, row, total, end)
+    for f in ("x", "y", "z", "r", "g", "b"):
+        assert np.array_equal(got[f].view(np.uint32 if f in "xyz" else np.uint8),
+                              want[f].view(np.uint32 if f in "xyz" else np.uint8)), f
+    # rows on the device: a count that is not a multiple of 32 and an output pointer that is not 16-byte aligned
+    rows = torch.zeros(total * 15 + 64, dtype=torch.uint8, device="cuda")
+    for n, off in ((total, 0), (total - 7, 1), (33, 5), (1, 3)):
+        rows.zero_()
+        assert ctx.cloud_to_ply_rows_dev(cloud.data_ptr(), n, rows.data_ptr() + off, cs) == n
+        torch.cuda.synchronize()
+        h = rows.cpu().numpy()
+        assert np.array_equal(np.frombuffer(h[off:off + n * 15].tobytes(), row), got[:n])
+        assert not h[off + n * 15:].any() and not h[:off].any()
+    assert ctx.save_ply(cloud.data_ptr(), 0, path) == 0
+
+
 def test_stitch_errors(ctx):
     rec = np.zeros((16, 5), np.int16)
     with pytest.raises(pcs.PcsError):
