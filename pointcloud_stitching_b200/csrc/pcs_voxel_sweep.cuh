@@ -2,22 +2,27 @@
 // own integer spec; the reference only #includes pcl/filters/voxel_grid.h,
 // src/pcs-multicamera-optimized.cpp:17).
 //
-//   1. sw_keys_hist   one read of the records: word[i] = (kz,ky,kx) << idx_bits | i  (one u64 carries
-//                     the voxel key AND the point index), pay[i] = colour + in-voxel offsets (one u64),
-//                     plus the digit histograms of every pass
+//   0. sw_bounds      occupied box of the cloud in voxel units (and, for the slab plan, a histogram
+//                     over z planes); the box fixes the key layout, so it is read back by the host
+//   1. sw_keys_hist   one read of the records: word[slot] = key << idx_bits | slot with the mixed-radix
+//                     key ((kz-z0)*dy + (ky-y0))*dx + (kx-x0) (one u64 carries the voxel key AND the
+//                     point's slot), pay[slot] = colour + in-voxel offsets (one u64), plus the digit
+//                     histograms of every pass; with a z-slab filter only the slab's points get slots
 //   2. sw_hist_scan   exclusive scan of each pass's histogram -> global bin bases
-//   3. sw_pass x P    one kernel per digit: each tile is read once and written once; tile-local
-//                     ranks from match_any, tile order from a ticket, the cross-tile prefix of every
-//                     digit from a decoupled look-back over per-tile status words (16 B/pt per pass)
+//   3. sw_pass x P    one kernel per 8-bit digit: each 4096-word tile arrives by one TMA bulk copy, is
+//                     ranked (per-bit ballots + per-warp counters), reordered in shared memory and written
+//                     once; tile order from a ticket, the cross-tile prefix of every digit from a two-level
+//                     decoupled look-back (16 B/pt per pass)
 //   4. sw_chunk_heads / sw_chunk_scan   voxel (segment) boundaries per 256-point chunk and their scan
-//   5. sw_reduce      one warp per chunk: gather pay[] through the sorted indices, warp-shuffle
+//   5. sw_reduce      one warp per chunk: gather pay[] through the sorted slots, warp-shuffle
 //                     segmented sums, integer means written straight to the output; only the segments
 //                     that cross a chunk boundary go through atomics into a per-chunk slot
 //   6. sw_finalize_open   integer means of those slots
 //
 // The sums are integers, so the result equals the CPU restatement bit for bit whatever the order
-// of the additions.  Needs 3*bits + ceil(log2 n) <= 64 and 24 + 3*ceil(log2 leaf) <= 64; the caller
-// falls back to the (key, idx) pair sort of pcs_voxel.cuh otherwise.
+// of the additions.  Needs key bits + slot bits <= 64 and 24 + 3*ceil(log2 leaf) <= 64; the caller
+// falls back to the (key, idx) pair sort of pcs_voxel.cuh otherwise.  Measurements and the tuning
+// history: profiles/r01_voxel.md.
 #pragma once
 #include <vector>
 

@@ -1,22 +1,25 @@
-"""Multi-GPU stitch: one process per GPU, cameras sharded in contiguous blocks, and an
-in-place gather of the packed XYZRGB records into the reference's stitched-buffer layout.
+"""Multi-GPU stitch: one process per GPU, cameras sharded in contiguous blocks, every rank ends a
+step holding the reference's stitched buffer of ALL cameras.
 
 The reference fans N camera streams into one host over TCP and concatenates them in
 camera-index order behind an int32 byte count
-(src/pcs-multicamera-client.cpp:381-395).  Here every rank's K1 writes its cameras'
-records straight into their slots of a replicated stitched buffer, so the "concat" is
-free, and the exchange is one collective over NVLink:
+(src/pcs-multicamera-client.cpp:381-395).  Here K1 writes every camera's records straight into
+its slot of a replicated stitched buffer, so the "concat" is free, and the exchange is one of:
 
-* fused (the product path, :class:`SymmetricStitchedSet`): the stitched buffers live in
-  symmetric memory, every rank's K1 launch stores each tile of records to its own copy AND
-  to the same offset of every peer's copy (TMA bulk stores over NVLink,
-  ``pcs_b200_batch_create_fanout``), so the all-gather happens inside the compute kernel,
-  tile by tile, with no second pass; one device-side barrier ends the step;
+* pull (the product path, :class:`SymmetricFrameSet`): the raw z16 + RGB8 frames live in symmetric
+  memory and every rank runs K1 over ALL cameras -- its own frames from HBM, the peers' through the
+  kernel's TMA loads from NVLink peer memory.  5 B/pt cross the link instead of 10 B/pt, the transfer
+  is the compute kernel's own input pipeline, and nobody writes into another rank's memory;
+* fused push (:class:`SymmetricStitchedSet`): the stitched buffers live in symmetric memory and
+  every rank's K1 stores each tile of records to its own copy AND to the same offset of every peer's
+  copy (TMA bulk stores over NVLink, ``pcs_b200_batch_create_fanout``);
 * NCCL baseline, equal shards  -> ``all_gather_into_tensor`` in place (send = recv + rank * count);
-* NCCL baseline, ragged shards -> one ``broadcast`` per rank of that rank's slot (all-gather-v),
+  ragged shards -> one ``broadcast`` per rank of that rank's slot (all-gather-v),
   e.g. 20 cameras on 8 GPUs = 3,3,3,3,2,2,2,2.
 
-torch.distributed is plumbing only (rendezvous, NCCL on GPUs, gloo in the CPU tests).
+:func:`sharded_voxel_merge` then downsamples the stitched cloud with every rank merging one z-slab
+of the voxel grid.  torch.distributed is plumbing only (rendezvous, symmetric-memory allocation,
+NCCL on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
 
