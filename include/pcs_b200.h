@@ -166,6 +166,14 @@ PCS_API int pcs_b200_batch_create_fanout(pcs_ctx *ctx, const pcs_frame_job *jobs
 /* Number of kernel launches one batch_run issues (for launch accounting). */
 PCS_API int pcs_b200_batch_launches(const pcs_batch *batch);
 
+/* Multi-GPU hosts that drive several GPUs from ONE process (one pcs_ctx per GPU): enables peer access
+ * from this context's device to peer_device, after which a job's z16_dev / color_dev may point at
+ * frames that live on the peer (the "pull" exchange: this GPU deprojects the peer's cameras itself,
+ * 5 B/pt over NVLink instead of receiving 10 B/pt of records) and the mirrors of
+ * pcs_b200_batch_create_fanout may be plain cudaMalloc memory of the peer.  Processes that own one
+ * GPU each map peer memory with CUDA IPC / symmetric memory instead. */
+PCS_API int pcs_b200_enable_peer(pcs_ctx *ctx, int peer_device);
+
 /* Device-pointer form of pcs_b200_pack_from_vertices. */
 PCS_API int pcs_b200_pack_from_vertices_dev(pcs_ctx *ctx, int stream, const float *xyz_dev,
                                     const float *uv_dev, int n, const uint8_t *color_dev,

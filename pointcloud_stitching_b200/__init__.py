@@ -118,6 +118,7 @@ def _load():
         "pcs_b200_batch_create": (C.c_int, [vp, C.POINTER(FrameJob), C.c_int, C.POINTER(vp)]),
         "pcs_b200_batch_create_fanout": (C.c_int, [vp, C.POINTER(FrameJob), C.c_int, vp, C.c_size_t,
                                                    C.POINTER(vp), C.c_int, C.POINTER(vp)]),
+        "pcs_b200_enable_peer": (C.c_int, [vp, C.c_int]),
         "pcs_b200_batch_run": (C.c_int, [vp, vp, vp]),
         "pcs_b200_batch_destroy": (None, [vp, vp]),
         "pcs_b200_batch_launches": (C.c_int, [vp]),
@@ -265,6 +266,10 @@ class Context:
         self._check(lib.pcs_b200_batch_create_fanout(self.handle, self._job_array(jobs), len(jobs), local_base,
                                                      local_bytes, peers, len(peer_bases), C.byref(h)))
         return Batch(self, h)
+
+    def enable_peer(self, peer_device):
+        """Single-process multi-GPU: let this context's kernels touch cudaMalloc memory of peer_device."""
+        self._check(lib.pcs_b200_enable_peer(self.handle, peer_device))
 
     def pack_from_vertices_dev(self, stream, xyz_ptr, uv_ptr, n, color_ptr, payload_ptr, count_ptr=None,
                                cuda_stream=0):

@@ -662,6 +662,25 @@ int pcs_b200_batch_create_fanout(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_
     return batch_create_impl(ctx, jobs, n_jobs, n_peers, delta, out);
 }
 
+// Lets this context's kernels read (pull exchange) and write (fan-out) memory that was cudaMalloc'ed
+// on another device of the same process.  Across processes the mapping comes from CUDA IPC / VMM /
+// symmetric memory instead and this call is not needed.
+int pcs_b200_enable_peer(pcs_ctx *ctx, int peer_device) {
+    if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
+    if (peer_device == ctx->device) return PCS_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int can = 0;
+    CU(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) return fail(ctx, PCS_ERR_UNSUPPORTED, "device %d cannot access device %d", ctx->device, peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return PCS_OK;
+    }
+    CU(ctx, e);
+    return PCS_OK;
+}
+
 int pcs_b200_batch_run(pcs_ctx *ctx, pcs_batch *b, void *cuda_stream) {
     if (!ctx || !b) return fail(ctx, PCS_ERR_INVALID, "null argument");
     cudaStream_t cs = (cudaStream_t)cuda_stream;

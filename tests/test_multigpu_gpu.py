@@ -112,3 +112,42 @@ def test_pull_fused_and_nccl_exchange_match_oracle(tmp_path, cams_total):
             want_vox = R.voxel_merge(want[4:].view(np.int16).reshape(-1, 5), 10)
             for r in range(world):
                 assert np.array_equal(np.load(os.path.join(str(tmp_path), "vox_r%d.npy" % r)), want_vox), r
+
+
+def test_single_process_pull_over_peer_access():
+    """A C++-style host: one process, one context per GPU, plain cudaMalloc frames.  After
+    pcs_b200_enable_peer every context deprojects ALL cameras -- its own frames from HBM, the other
+    GPU's over NVLink -- and both stitched buffers must equal the oracle's."""
+    import oracle
+    import pointcloud_stitching_b200 as pcs
+    from pointcloud_stitching_b200 import multigpu, synth
+    R = oracle.restatement()
+    cams, world = 4, 2
+    layout = multigpu.StitchLayout([W * H] * cams, world)
+    cal = oracle.make_calib(W, H, translation=synth.D2C_BASELINE)
+    want = R.concat([R.frame(cal, synth.depth_frame(W, H, cam, 0), synth.color_frame(W, H, cam, 0), 3, W * 3,
+                             synth.TF_STITCH[cam % 8]) for cam in range(cams)], 1)
+    frames = {}
+    for r in range(world):
+        for cam in layout.cams_of[r]:
+            frames[cam] = (torch.from_numpy(synth.depth_frame(W, H, cam, 0).view(np.int16)).to("cuda:%d" % r),
+                           torch.from_numpy(synth.color_frame(W, H, cam, 0)).to("cuda:%d" % r))
+    for r in range(world):
+        torch.cuda.synchronize(r)
+    ctxs, bufs = [], []
+    for r in range(world):
+        ctx = pcs.Context(device=r, max_streams=cams)
+        ctx.enable_peer(1 - r)
+        ctx.enable_peer(1 - r)          # idempotent
+        for cam in range(cams):
+            ctx.set_stream(cam, pcs.stream_desc(W, H, tf=synth.TF_STITCH[cam % 8], translation=synth.D2C_BASELINE))
+        buf = multigpu.StitchedBuffer(layout, r, torch.device("cuda", r))
+        batch = ctx.batch([(cam, frames[cam][0].data_ptr(), frames[cam][1].data_ptr(), buf.slot_ptr(cam))
+                           for cam in range(cams)])
+        with torch.cuda.device(r):
+            batch.run(torch.cuda.current_stream(r).cuda_stream)
+        ctxs.append((ctx, batch))
+        bufs.append(buf)
+    for r in range(world):
+        torch.cuda.synchronize(r)
+        assert np.array_equal(bufs[r].wire_bytes().cpu().numpy(), want), r
