@@ -329,7 +329,7 @@ template <int BITS, int THREADS, int ITEMS, bool BALLOT>
 __global__ void __launch_bounds__(THREADS, (BITS > 8 || THREADS > 256 ? 2 : (ITEMS <= 8 ? 4 : 3)))
 sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n, int shift,
         const uint32_t *__restrict__ gbase, uint32_t *status, uint32_t *gstatus,
-        int n_tiles, uint32_t *ticket, uint32_t *err, int probe) {
+        int n_tiles, uint32_t *ticket, uint32_t *err, int probe, int poll_ns) {
     using Cfg = SweepPassCfg<BITS, THREADS, ITEMS>;
     constexpr int BINS = Cfg::BINS, WARPS = Cfg::WARPS, TILE = Cfg::TILE, DPT = Cfg::DPT;
     extern __shared__ __align__(16) uint8_t sw_smem[];
@@ -514,7 +514,7 @@ sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n, int 
             }
             if (!progress) {
                 if (++spins >= SW_SPIN_LIMIT) { atomicExch(err, 1u); break; }
-                __nanosleep(64);      // polling in a tight loop starves the tiles being waited for
+                if (poll_ns) __nanosleep(poll_ns);      // polling in a tight loop starves the tiles being waited for
             }
         }
         gdelta[d] = gbase[d] + before_group + in_group - tile_excl[d];
@@ -994,11 +994,12 @@ inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int lea
     sw_hist_scan<BITS><<<passes, BINS, 0, cs>>>(ghist);
     static const bool ballot = pipe_knob("PCS_SW_BALLOT", 1, 0, 1) != 0;     // 0: MATCH.ANY ranking (tuning knob)
     static const int probe = pipe_knob("PCS_SW_PROBE", 0, 0, 15);            // timing probes (wrong results!)
+    static const int poll_ns = pipe_knob("PCS_SW_POLL_NS", 512, 0, 4096);     // pause between look-back polls (0/64/200/600/1500 ns: 1.118/1.101/1.092/1.067/1.074 ms)
     for (int p = 0; p < passes; ++p) {
         auto kern = ballot ? sw_pass<BITS, THREADS, ITEMS, true> : sw_pass<BITS, THREADS, ITEMS, false>;
         kern<<<n_tiles, THREADS, Cfg::SMEM, cs>>>(
             w0, w1, m, g.idx_bits + p * BITS, ghist + (size_t)p * BINS, status + (size_t)p * n_tiles * BINS,
-            gstatus + (size_t)p * groups_max * BINS, n_tiles, ticket + p, err, probe);
+            gstatus + (size_t)p * groups_max * BINS, n_tiles, ticket + p, err, probe, poll_ns);
         std::swap(w0, w1);
     }
     const int cblocks = (n_chunks + 7) / 8;
