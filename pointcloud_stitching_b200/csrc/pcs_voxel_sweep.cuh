@@ -375,9 +375,9 @@ sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n, int 
             if (tbase + j < n) raw[j] = in[tbase + j];
         __syncthreads();
     }
-    // lanes holding the same digit, from one ballot per digit bit (MATCH.ANY is no faster and occupies
-    // a per-SM unit for ~35 cycles per warp instruction).  All masks first -- the ballots of different
-    // items are independent -- then the serial walk over the warp's counters.
+    // lanes holding the same digit, from one ballot per digit bit (MATCH.ANY, PCS_SW_BALLOT=0, measured
+    // the same: 151 vs 145 us per pass -- the pass is latency-bound).  All masks first -- the ballots of
+    // different items are independent -- then the serial walk over the warp's counters.
     uint32_t mask[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
