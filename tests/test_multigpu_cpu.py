@@ -28,6 +28,32 @@ def test_partition_and_layout():
         multigpu.StitchLayout([921600] * 300, 8)      # > int32 header
 
 
+def test_partition_and_layout_properties():
+    """For any camera count / world size: contiguous blocks in camera order, sizes differ by at most one,
+    rank byte ranges tile the payload exactly, and every camera has exactly one owner."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 64), st.integers(1, 16), st.integers(1, 4096))
+    def check(n_cams, world, pts):
+        blocks = multigpu.partition(n_cams, world)
+        assert len(blocks) == world and [c for b in blocks for c in b] == list(range(n_cams))
+        sizes = [len(b) for b in blocks]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+        L = multigpu.StitchLayout([pts * 8] * n_cams, world)
+        assert L.total_bytes == n_cams * pts * 80
+        pos = 0
+        for r in range(world):
+            if L.rank_bytes[r]:
+                assert L.rank_offset[r] == pos
+            pos += L.rank_bytes[r]
+        assert pos == L.total_bytes
+        assert all(L.rank_of(c) == r for r, b in enumerate(blocks) for c in b)
+        assert L.equal == (n_cams % world == 0)
+
+    check()
+
+
 def test_pull_exchange_job_table():
     """The pull exchange's host logic: frame slots do not overlap, and every rank's job table names
     every camera once per frame, reading the owner's allocation and writing the local stitched slot."""
