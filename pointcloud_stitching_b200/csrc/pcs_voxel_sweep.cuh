@@ -993,7 +993,11 @@ inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int lea
         sw_keys_hist<BITS, false><<<kh_grid, SW_KH_THREADS, (size_t)passes * BINS * 4, cs>>>(rec, n, g, passes, w0, pay, ghist, slot_counter);
     sw_hist_scan<BITS><<<passes, BINS, 0, cs>>>(ghist);
     static const bool ballot = pipe_knob("PCS_SW_BALLOT", 1, 0, 1) != 0;     // 0: MATCH.ANY ranking (tuning knob)
-    static const int probe = pipe_knob("PCS_SW_PROBE", 0, 0, 15);            // timing probes (wrong results!)
+#ifdef PCS_SW_PROBES      // timing probes skip phases of sw_pass (WRONG results): only in builds made for tools/probe_vox.py
+    static const int probe = pipe_knob("PCS_SW_PROBE", 0, 0, 15);
+#else
+    constexpr int probe = 0;
+#endif
     static const int poll_ns = pipe_knob("PCS_SW_POLL_NS", 512, 0, 4096);     // pause between look-back polls (0/64/200/600/1500 ns: 1.118/1.101/1.092/1.067/1.074 ms)
     for (int p = 0; p < passes; ++p) {
         auto kern = ballot ? sw_pass<BITS, THREADS, ITEMS, true> : sw_pass<BITS, THREADS, ITEMS, false>;

@@ -1,6 +1,7 @@
 """Timing probe for the voxel merge: whole-merge time on 14.7 M uniform random points under the tuning knobs
-PCS_SW_PROBE (bit 0: skip the look-back, 1: skip the stores, 2: skip the ranking -- results are then WRONG, only
-the time means anything), PCS_SW_BALLOT (0 = MATCH.ANY ranking), PCS_SW_POLL_NS and VV (voxel_variant).
+PCS_SW_PROBE (needs a library built with `make -C pointcloud_stitching_b200/csrc -B PTXAS=-DPCS_SW_PROBES`;
+bit 0: skip the look-back, 1: skip the stores, 2: skip the ranking -- results are then WRONG, only the time
+means anything), PCS_SW_BALLOT (0 = MATCH.ANY ranking), PCS_SW_POLL_NS and VV (voxel_variant).
 Results: profiles/r01_voxel.md."""
 import os, sys, numpy as np, torch
 sys.path.insert(0, os.environ.get("GRAFT_REPO_ROOT", "/root/repo"))
