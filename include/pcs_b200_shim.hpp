@@ -10,6 +10,8 @@
 #pragma once
 #include <sys/socket.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -63,6 +65,48 @@ inline pcs_stream_desc make_stream_desc(const pcs_intrinsics &depth, const pcs_i
     d.z_lo = 0.f; d.z_hi = 1.5f; d.x_lo = -2.f; d.x_hi = 2.f;
     d.cutoff_lane_reversed = 1;   // what the reference's -m -c actually does
     return d;
+}
+
+// The camera -> world transform of one camera from a calibration file instead of a constant pasted
+// into the source (the reference: calibration/camera_alignment.py prints `transform[k] << ...` for
+// src/pcs-multicamera-optimized.cpp:417-455 and tf_mat, src/pcs-camera-optimized.cpp:64-67 -- a
+// recompile per rig).  The file is what pointcloud_stitching_b200/calibration.py writes:
+//     { "CAMERA": [[r00, r01, r02, tx], [r10, ...], [r20, ...], [0, 0, 0, 1]], ... }
+// Returns false when the file cannot be read or does not hold 16 numbers under that name.
+inline bool load_transform(const std::string &path, const std::string &camera, float tf[16]) {
+    std::FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::string text;
+    char buf[4096];
+    size_t got;
+    while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, got);
+    std::fclose(f);
+    const std::string key = "\"" + camera + "\"";
+    size_t at = 0;
+    while ((at = text.find(key, at)) != std::string::npos) {
+        size_t p = at + key.size();
+        while (p < text.size() && (text[p] == ' ' || text[p] == '\n' || text[p] == '\r' || text[p] == '\t')) ++p;
+        if (p < text.size() && text[p] == ':') {      // a key, not a value that happens to match
+            ++p;
+            int n = 0;
+            while (p < text.size() && n < 16) {
+                const char c = text[p];
+                if (c == '[' || c == ',' || c == ' ' || c == '\n' || c == '\r' || c == '\t') { ++p; continue; }
+                if (c == ']') {                        // rows close with ']'; "]]" ends the matrix
+                    ++p;
+                    continue;
+                }
+                char *end = nullptr;
+                const double v = std::strtod(text.c_str() + p, &end);
+                if (end == text.c_str() + p) break;    // not a number: malformed
+                tf[n++] = (float)v;
+                p = (size_t)(end - text.c_str());
+            }
+            return n == 16;
+        }
+        at = p;
+    }
+    return false;
 }
 
 // int copyPointCloudXYZRGBToBufferSIMD(rs2::points&, const rs2::video_frame&, short*)

@@ -6,7 +6,7 @@
 // frame without waiting for pulls, like `pcs-camera-optimized -f X -s` (:264-302).
 //
 //   pcs_camera_node --depth d.raw --color c.raw --w 1280 --h 720 --frames 4 [--port 8000]
-//                   [--tx 0.015] [--tf k] [--push] [--loops n]
+//                   [--tx 0.015] [--tf k | --tf-file transforms.json --camera NAME] [--push] [--loops n]
 //
 // Host code only: everything per-frame happens inside pcs_b200::sendXYZRGBPointcloudFused.
 #include <netinet/in.h>
@@ -50,7 +50,7 @@ bool read_file(const std::string &path, std::vector<uint8_t> &out, size_t bytes)
 }  // namespace
 
 int main(int argc, char **argv) {
-    std::string depth_path, color_path;
+    std::string depth_path, color_path, tf_file, camera;
     int w = 1280, h = 720, frames = 1, port = 8000, tf = 0, loops = 1 << 30;
     float tx = 0.f;
     bool push = false;
@@ -65,6 +65,8 @@ int main(int argc, char **argv) {
         else if (a == "--port") port = atoi(next());
         else if (a == "--tx") tx = (float)atof(next());
         else if (a == "--tf") tf = atoi(next());
+        else if (a == "--tf-file") tf_file = next();      // written by pointcloud_stitching_b200/calibration.py
+        else if (a == "--camera") camera = next();
         else if (a == "--loops") loops = atoi(next());
         else if (a == "--push") push = true;
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
@@ -79,7 +81,16 @@ int main(int argc, char **argv) {
         pcs_b200::Context ctx(1);
         pcs_intrinsics in = {w, h, (w - 1) / 2.f, (h - 1) / 2.f, w / 2.f, w / 2.f};
         const float rot[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tr[3] = {tx, 0.f, 0.f};
-        ctx.set_stream(0, pcs_b200::make_stream_desc(in, in, rot, tr, 0.001f, 3, w * 3, TF[tf ? 1 : 0], false));
+        float tf_loaded[16];
+        const float *tf_mat = TF[tf ? 1 : 0];
+        if (!tf_file.empty()) {
+            if (!pcs_b200::load_transform(tf_file, camera, tf_loaded)) {
+                fprintf(stderr, "no transform for camera '%s' in %s\n", camera.c_str(), tf_file.c_str());
+                return 2;
+            }
+            tf_mat = tf_loaded;
+        }
+        ctx.set_stream(0, pcs_b200::make_stream_desc(in, in, rot, tr, 0.001f, 3, w * 3, tf_mat, false));
 
         // initSocket (:75-105): bind, listen, accept exactly one client
         int srv = socket(AF_INET, SOCK_STREAM, IPPROTO_TCP), one = 1;

@@ -45,3 +45,27 @@ def test_reference_label_convention_and_roundtrip(tmp_path):
     back = calibration.load_transforms(str(out))
     assert back["A"].dtype == np.float32 and back["A"].shape == (16,)
     assert np.allclose(back["A"].reshape(4, 4), tfs["A"], atol=1e-6)
+
+
+def test_cxx_host_loads_the_same_transforms(tmp_path):
+    """include/pcs_b200_shim.hpp::load_transform (used by pcs_camera_node --tf-file/--camera) reads the
+    JSON calibration.py writes and yields the same float32 values as load_transforms."""
+    import subprocess
+    from conftest import ROOT
+    tfs = calibration.transforms_from_csv(os.path.join(GOLDEN, "pcs4_markers.csv"))
+    tfs["E-7"] = np.array([[1e-9, -2.5e3, 3, 4], [5, 6e-12, 7, -8], [9, 10, 11, 12.125], [0, 0, 0, 1]])
+    js = tmp_path / "rig.json"
+    calibration.save_transforms(str(js), tfs)
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "tf_json_main")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["/usr/bin/g++", "-std=c++11", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "tf_json_main.cpp"), "-o", exe],
+                   check=True, capture_output=True, text=True)
+    want = calibration.load_transforms(str(js))
+    for name in tfs:
+        r = subprocess.run([exe, str(js), name], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout
+        got = np.array([int(x, 16) for x in r.stdout.split()], np.uint32).view(np.float32)
+        assert np.array_equal(got, want[name]), name
+    assert subprocess.run([exe, str(js), "NOPE"], capture_output=True, text=True).returncode == 1
+    assert subprocess.run([exe, str(tmp_path / "missing.json"), "LEVO"], capture_output=True).returncode == 1
