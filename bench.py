@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- Mpoints/s stitched on synthetic 1280x720 depth+RGB streams.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--tex baseline|aligned|rotated|color1080p]
 
-One "step" = one pass of the hot path (depth deprojection + 4x4 transform + colour
-attach + int16 pack, fused kernel K1) over one batch of STREAMS x FRAMES synthetic
-frames per GPU (default 8 x 8 = 64 frames = 59.0 Mpoints, 885 MB of algorithmic
-traffic -- seven times the 126 MB L2, so every step streams from HBM).  With N > 1
-(torchrun, one rank per GPU) every rank runs its own 8 streams (weak scaling) and
-the packed records are all-gathered over NVLink into the stitched buffer.
+Headline ("value"): one "step" = one pass of the hot path (depth deprojection + 4x4 transform + colour
+attach + int16 pack, fused kernel K1) over one batch of STREAMS x FRAMES synthetic frames per GPU
+(default 8 x 8 = 64 frames = 59.0 Mpoints, 885 MB of algorithmic traffic -- seven times the 126 MB L2,
+so every step streams from HBM).  With N > 1 (torchrun, one rank per GPU) every rank owns 8 streams
+(weak scaling) and ends each step holding the stitched buffer of ALL N x 8 cameras (exchange fused
+into K1's input pipeline over NVLink); the stitched bytes are verified once per run on every rank
+("stitched_check").
 
-Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events, max over
-ranks) with inputs resident in HBM; `e2e` goes through the reference-facing C ABI
-call (pcs_b200_send_xyzrgb: host buffers in, host camera buffer out), host<->device
-copies inside the timed region.  `--impl reference` times the reference's own CPU
-implementation (oracle/_ref: src/pcs-camera-optimized.cpp compiled unmodified) on
-the host cores instead.
+The same JSON line carries, under "configs", BASELINE.json's other single-box configurations as
+self-checking measurements: c3 (4 x 1280x720 on one GPU: K1 -> in-place concat -> 10 mm voxel merge) and
+c5 (20 x 848x480 on the run's N GPUs: K1 -> exchange -> sharded voxel merge), each with its own
+roofline and cpu_baseline.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events, max over ranks) with inputs
+resident in HBM; `e2e` goes through the reference-facing C ABI with HOST buffers (host<->device copies
+inside the timed region).  `--impl reference` times the reference's own CPU implementation
+(oracle/_ref: src/pcs-camera-optimized.cpp compiled unmodified) on the host cores, on the same
+config; that arm never loads the product library.
 """
 import argparse
 import json
@@ -34,6 +39,8 @@ W, H = 1280, 720
 NPTS = W * H
 ALG_BYTES_PER_POINT = 15          # 2 (z16) + 3 (RGB8) + 10 (record), SURVEY s8(d)
 METRIC = "Mpoints/sec stitched (1280x720xN cams)"
+LEAF_MM = 10
+TEX_CHOICES = ["baseline", "aligned", "rotated", "color1080p"]
 
 
 def parse():
@@ -45,15 +52,19 @@ def parse():
     ap.add_argument("--streams", type=int, default=8, help="camera streams per GPU")
     ap.add_argument("--frames", type=int, default=8, help="frames per stream per step")
     ap.add_argument("--variant", type=int, default=0, help="kernel_variant: 0 auto, 1 direct, 2 pipelined")
-    ap.add_argument("--tex", default="baseline", choices=["baseline", "aligned"],
-                    help="depth->colour extrinsics: 15 mm baseline (D435-like) or identity")
+    ap.add_argument("--tex", default="baseline", choices=TEX_CHOICES,
+                    help="depth->colour calibration: 15 mm baseline (D435-like), identity, 15 mm + small rotation, "
+                         "or 15 mm + 1920x1080 colour (what the reference records, src/pcs-camera-grab-frames.cpp:69-70)")
     ap.add_argument("--exchange", default="pull", choices=["pull", "fused", "nccl"],
                     help="N > 1: pull = every rank runs K1 over all cameras, reading the peers' raw frames over NVLink "
                          "(5 B/pt on the link); fused = K1 stores every tile of records to all peers (10 B/pt); "
                          "nccl = K1 then all-gather")
+    ap.add_argument("--configs", default="c3,c5", help="extra BASELINE configs measured into the same line ('none' to skip)")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the sustained K1 leg (0 to skip)")
     ap.add_argument("--e2e-depth", type=int, default=2, choices=[1, 2], help="frames in flight per camera in the e2e leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the stitched-bytes verification")
     return ap.parse_args()
 
 
@@ -68,13 +79,18 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram read+write bytes per launch of the dominant kernel from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r01_k1_ncu_summary.json")
-    try:
-        return json.load(open(p)).get("dram_bytes_per_launch")
-    except Exception:
-        return None
+def ncu_traffic(name):
+    """dram read+write bytes per launch of a kernel from a committed ncu capture (not measured in this
+    run: ncu cannot run inside the timed process).  Returns (bytes or None, source label)."""
+    for rnd in ("r02", "r01"):
+        rel = os.path.join("profiles", "%s_%s_ncu_summary.json" % (rnd, name))
+        try:
+            v = json.load(open(os.path.join(ROOT, rel))).get("dram_bytes_per_launch")
+            if v is not None:
+                return v, rel + " (ncu --set full capture of the same launch, committed)"
+        except Exception:
+            pass
+    return None, None
 
 
 class ClockSampler:
@@ -94,6 +110,7 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def stop(self):
         if not self.proc:
@@ -121,80 +138,309 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_frames(streams, frames, rank):
+# ---- the synthetic calibration of a --tex choice (shared by both arms and the oracle) -----------
+def tex_calibration(tex):
+    """dict(cw, ch, translation, rotation) -- colour geometry and depth->colour extrinsics."""
     from pointcloud_stitching_b200 import synth
-    d = np.empty((streams, frames, H, W), np.uint16)
-    c = np.empty((streams, frames, H, W * 3), np.uint8)
+    cal = {"cw": W, "ch": H, "translation": synth.D2C_BASELINE, "rotation": None}
+    if tex == "aligned":
+        cal["translation"] = (0.0, 0.0, 0.0)
+    elif tex == "rotated":
+        cal["rotation"] = synth.D2C_ROTATION_SMALL
+    elif tex == "color1080p":
+        cal["cw"], cal["ch"] = 1920, 1080
+    return cal
+
+
+def tex_label(tex):
+    return {"baseline": "15 mm baseline", "aligned": "identity", "rotated": "15 mm baseline + 0.3 deg rotation",
+            "color1080p": "15 mm baseline, 1920x1080 colour"}[tex]
+
+
+def headline_config(args, world):
+    """`config` of the JSON line: identical for the b200 arm and the reference arm of the same command."""
+    S, F = args.streams, args.frames
+    cal = tex_calibration(args.tex)
+    return {"workload": "%d streams/GPU x %d frames x 1280x720 z16 depth + %dx%d RGB8 per step: fused deproject + "
+                        "transform + colour + int16 pack, stitched in camera order; depth->colour: %s" % (
+                            S, F, cal["cw"], cal["ch"], tex_label(args.tex)),
+            "streams_per_gpu": S, "frames_per_step": F, "points_per_step": world * S * F * NPTS, "tex": args.tex,
+            "l2": "working set %.0f MB per step per GPU >> 126 MB L2 (distinct inputs, no flush needed)" % (
+                ALG_BYTES_PER_POINT * S * F * NPTS / 1e6)}
+
+
+def make_frames(streams, frames, rank, cw=W, ch=H, w=W, h=H, first_cam=None):
+    from pointcloud_stitching_b200 import synth
+    first = rank * streams if first_cam is None else first_cam
+    d = np.empty((streams, frames, h, w), np.uint16)
+    c = np.empty((streams, frames, ch, cw * 3), np.uint8)
     for s in range(streams):
         for f in range(frames):
-            d[s, f] = synth.depth_frame(W, H, rank * streams + s, f)
-            c[s, f] = synth.color_frame(W, H, rank * streams + s, f)
+            d[s, f] = synth.depth_frame(w, h, first + s, f)
+            c[s, f] = synth.color_frame(cw, ch, first + s, f)
     return d, c
 
 
 # ------------------------------------------------------------------------------------
-def cpu_reference(threads, sample_frames, tex):
-    """The reference CPU path on `sample_frames` 1280x720 frames with `threads` OpenMP threads:
-    stub rs2::pointcloud::calculate (oracle restatement of librealsense, threaded the same way)
-    + the reference's own sendXYZRGBPointcloud (-m).  Returns dict."""
+def cpu_reference(threads, frames, tex, d_np=None, c_np=None):
+    """The reference CPU path over `frames` DISTINCT 1280x720 frames with `threads` OpenMP threads:
+    stub rs2::pointcloud::calculate (oracle restatement of librealsense, threaded the same way) + the
+    reference's own sendXYZRGBPointcloud (-m -t threads, oracle/_ref).  Returns dict."""
     import oracle
     from pointcloud_stitching_b200 import synth
     R = oracle.restatement()
     RC = oracle.ref_camera()
-    trans = synth.D2C_BASELINE if tex == "baseline" else (0.0, 0.0, 0.0)
-    cal = oracle.make_calib(W, H, translation=trans)
-    z, col = synth.depth_frame(W, H, 0, 0), synth.color_frame(W, H, 0, 0)
-    t_calc = []
-    xyz = uv = None
-    for _ in range(3 + sample_frames):
+    cal_d = tex_calibration(tex)
+    cw, ch = cal_d["cw"], cal_d["ch"]
+    cal = oracle.make_calib(W, H, cw, ch, translation=cal_d["translation"], rotation=cal_d["rotation"])
+    if d_np is None:
+        n_src = min(frames, 8)
+        d_np, c_np = make_frames(1, n_src, 0, cw, ch)
+    d_flat, c_flat = d_np.reshape(-1, H, W), c_np.reshape(-1, ch, cw * 3)
+    kind = "reference" if RC is not None else "port"
+    if RC is None:
+        threads = 1
+    t_calc, t_pack = [], []
+    for i in range(2 + frames):
+        z, col = d_flat[i % len(d_flat)], c_flat[i % len(c_flat)]
         t0 = time.perf_counter()
         xyz, uv = R.deproject(cal, z, threads)
-        t_calc.append((time.perf_counter() - t0) * 1e3)
-    t_calc = t_calc[3:]
-    if RC is not None:
-        kind = "reference"
-        RC.time_send(xyz, uv, col, W, H, 3, W * 3, synth.TF_CAMERA, 3, threads=threads)
-        t_pack = list(RC.time_send(xyz, uv, col, W, H, 3, W * 3, synth.TF_CAMERA, sample_frames, threads=threads))
-    else:
-        kind = "port"
-        t_pack = []
-        for _ in range(3 + sample_frames):
-            t0 = time.perf_counter()
-            R.send(xyz, uv, col, W, H, 3, W * 3, synth.TF_CAMERA)
-            t_pack.append((time.perf_counter() - t0) * 1e3)
-        t_pack = t_pack[3:]
-        threads = 1
-    calc, pack = float(np.median(t_calc)), float(np.median(t_pack))
-    return {"value": NPTS / ((calc + pack) * 1e-3) / 1e6, "unit": "Mpoints/s", "cores": threads, "kind": kind,
-            "sample": "%d frames 1280x720, median per frame: deproject (oracle restatement of rs2::pointcloud::"
-                      "calculate) %.3f ms + sendXYZRGBPointcloud -m -t %d %.3f ms" % (sample_frames, calc, threads, pack),
-            "pack_only_mpoints_s": NPTS / (pack * 1e-3) / 1e6, "deproject_ms": calc, "pack_ms": pack,
-            "host_cores": os.cpu_count()}
+        t1 = time.perf_counter()
+        if RC is not None:
+            ms = float(RC.time_send(xyz, uv, col, cw, ch, 3, cw * 3, synth.TF_CAMERA, 1, threads=threads)[0])
+        else:
+            t2 = time.perf_counter()
+            R.send(xyz, uv, col, cw, ch, 3, cw * 3, synth.TF_CAMERA)
+            ms = (time.perf_counter() - t2) * 1e3
+        if i >= 2:
+            t_calc.append((t1 - t0) * 1e3)
+            t_pack.append(ms)
+    calc, pack = float(np.sum(t_calc)), float(np.sum(t_pack))
+    return {"value": frames * NPTS / ((calc + pack) * 1e-3) / 1e6, "unit": "Mpoints/s", "cores": threads, "kind": kind,
+            "sample": "%d distinct frames 1280x720 (%s), per frame: deproject (oracle restatement of rs2::pointcloud::"
+                      "calculate) %.3f ms + sendXYZRGBPointcloud -m -t %d %.3f ms" % (
+                          frames, tex, calc / frames, threads, pack / frames),
+            "pack_only_mpoints_s": frames * NPTS / (pack * 1e-3) / 1e6, "deproject_ms": calc / frames,
+            "pack_ms": pack / frames, "total_ms": calc + pack, "host_cores": os.cpu_count()}
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation on this box's host cores, same config.  Loads
+    oracle/ only -- never the product library (pointcloud_stitching_b200.lib is lazy and untouched here)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = max(1, args.gpus)
     threads = os.cpu_count() or 1
-    per_step = args.streams                      # one frame per stream: a bounded sample of the step
+    S, F = args.streams, args.frames
+    cal = tex_calibration(args.tex)
+    d_np, c_np = make_frames(S, F, 0, cal["cw"], cal["ch"])
+    frames_step_full = world * S * F
+    frames_sample = S * F            # one GPU's share of the step, all S x F distinct frames, every step
     vals = []
     info = None
     for i in range(args.warmup + args.steps):
-        info = cpu_reference(threads, per_step, args.tex)
+        info = cpu_reference(threads, frames_sample, args.tex, d_np, c_np)
         if i >= args.warmup:
             vals.append(info["value"])
     v = float(np.median(vals))
-    ms = per_step * NPTS / (v * 1e6) * 1e3
+    ms = frames_step_full * NPTS / (v * 1e6) * 1e3
     info["value"] = v
+    info["sample"] = ("every step: %d of the step's %d frames (all %d x %d distinct frames of one GPU's share), all %d host "
+                      "threads; ms_per_step is scaled to the full step; last step: %s" % (
+                          frames_sample, frames_step_full, S, F, threads, info["sample"]))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mpoints/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%d streams x 1280x720 depth+RGB8, d2c=%s; each step is a bounded sample of "
-                                   "%d frames (one per stream) on the host cores" % (args.streams, args.tex, per_step)},
+            "config": headline_config(args, world),
             "cpu_baseline": info,
-            "e2e": {"value": v, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": v, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "product_library_loaded": "libpcs_b200" in open("/proc/self/maps").read()}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------
+class Timer:
+    """CUDA-event timing on torch's current stream, max over ranks."""
+
+    def __init__(self, torch, dist, world):
+        self.torch, self.dist, self.world = torch, dist, world
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, fn, iters, warm=3):
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / iters
+
+
+def stream_descs(pcs, synth, tex, n_cams, w=W, h=H):
+    cal = tex_calibration(tex)
+    cw, ch = (cal["cw"], cal["ch"]) if (w, h) == (W, H) else (w, h)
+    return [pcs.stream_desc(w, h, cw, ch, tf=synth.TF_STITCH[cam % 8], translation=cal["translation"],
+                            rotation=cal["rotation"]) for cam in range(n_cams)]
+
+
+def oracle_records(tex, cam, z, col, w=W, h=H):
+    """CPU oracle of K1 for one frame (the checker; never timed as product)."""
+    import oracle
+    from pointcloud_stitching_b200 import synth
+    cal = tex_calibration(tex)
+    cw, ch = (cal["cw"], cal["ch"]) if (w, h) == (W, H) else (w, h)
+    R = oracle.restatement()
+    c = oracle.make_calib(w, h, cw, ch, translation=cal["translation"], rotation=cal["rotation"])
+    return R.frame(c, z, col, 3, cw * 3, synth.TF_STITCH[cam % 8])
+
+
+# ---- config #3: 4 x 1280x720 on one GPU, K1 -> in-place concat -> voxel merge ------------------
+def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, world, local, timer, peak):
+    """c3: 4 x 1280x720, one GPU.  c5: 20 x 848x480 on `world` GPUs (BASELINE.json configs #3 / #5).
+    Step = `frames` stitched frames: per frame one K1 launch writes every camera's slot of the stitched buffer
+    (the concat costs nothing) and the stitched records are merged on a 10 mm voxel grid."""
+    if name == "c3":
+        cams, w, h, frames = 4, 1280, 720, 8
+        if world > 1:
+            return None      # a single-GPU configuration
+    else:
+        cams, w, h, frames = 20, 848, 480, 4
+    npts = w * h
+    dev = torch.device("cuda", local)
+    cs = torch.cuda.current_stream().cuda_stream
+    n = cams * npts
+    layout = multigpu.StitchLayout([npts] * cams, world)
+    ctx = pcs.Context(device=local, max_streams=cams, kernel_variant=args.variant)
+    stride = ((w * 3 + 15) // 16) * 16
+    for cam in range(cams):
+        d = pcs.stream_desc(w, h, tf=synth.TF_STITCH[cam % 8], translation=synth.D2C_BASELINE)
+        d.color_stride = stride
+        ctx.set_stream(cam, d)
+    stitched = [multigpu.StitchedBuffer(layout, rank, dev) for _ in range(frames)]
+    keep = []
+    if world > 1:
+        fset = multigpu.SymmetricFrameSet(layout, rank, dev, w, h, frames, stride=stride)
+        for cam in layout.cams_of[rank]:
+            for f in range(frames):
+                col = np.zeros((h, stride), np.uint8)
+                col[:, :w * 3] = synth.color_frame(w, h, cam, f)
+                fset.upload(cam, f, synth.depth_frame(w, h, cam, f), col)
+        torch.cuda.synchronize()
+        fset.barrier()
+        pj = fset.pull_jobs(stitched)      # frame-major: [f * cams + cam]
+        batches = [ctx.batch(pj[f * cams:(f + 1) * cams]) for f in range(frames)]
+    else:
+        fset = None
+        batches = []
+        for f in range(frames):
+            jobs = []
+            for cam in range(cams):
+                col = np.zeros((h, stride), np.uint8)
+                col[:, :w * 3] = synth.color_frame(w, h, cam, f)
+                z = torch.from_numpy(synth.depth_frame(w, h, cam, f).view(np.int16)).to(dev)
+                c = torch.from_numpy(col).to(dev)
+                keep.append((z, c))
+                jobs.append((cam, z.data_ptr(), c.data_ptr(), stitched[f].slot_ptr(cam)))
+            batches.append(ctx.batch(jobs))
+    outs = [torch.zeros(n * 5, dtype=torch.int16, device=dev) for _ in range(frames)]
+    nv = [0] * frames
+
+    def k1_only():
+        for f in range(frames):
+            batches[f].run(cs)
+        if fset is not None:
+            fset.barrier()
+
+    def merge_only():
+        for f in range(frames):
+            total, mine = multigpu.sharded_voxel_merge(ctx, stitched[f].payload.data_ptr(), n, LEAF_MM, rank, world,
+                                                       outs[f], cs, gather=False)
+            nv[f] = mine
+
+    def step():
+        k1_only()
+        merge_only()
+
+    iters = max(3, min(args.steps, 10))
+    ms_step = timer.run(step, iters)
+    ms_k1 = timer.run(k1_only, iters)
+    ms_merge = timer.run(merge_only, iters)
+    # voxels over all ranks (each rank keeps its z-slab of the grid)
+    nv_local = torch.tensor([float(sum(nv))], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(nv_local)
+    nv_total = int(nv_local.item())
+    pts_step = n * frames
+    # roofline of the merge, SURVEY s8(d): lower bound 10 B/pt read + 10 B/voxel written
+    alg = 10.0 * pts_step / world + 10.0 * sum(nv)
+    achieved = alg / (ms_merge * 1e-3) / 1e9
+    res = {"workload": "%d cams x %dx%d, %d stitched frames per step, K1 -> in-place concat -> voxel-grid merge %d mm%s" % (
+               cams, w, h, frames, LEAF_MM, "" if world == 1 else " (pull exchange; merge sharded by z-slab, slabs stay on their GPUs)"),
+           "n_gpus": world, "points_per_step": pts_step, "voxels_per_step": nv_total,
+           "value": pts_step / (ms_step * 1e-3) / 1e6, "unit": "Mpoints/s", "ms_per_step": ms_step,
+           "k1_ms_per_step": ms_k1, "merge_ms_per_step": ms_merge, "merge_ms_per_frame": ms_merge / frames,
+           "gpu_launches_per_step": None,
+           "roofline": {"bound": "hbm", "kernel": "voxel merge (sw_keys_hist + sw_pass x P + sw_reduce; sw_pass dominant)",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "algorithmic_bytes_per_step_per_gpu": alg, "traffic": None,
+                        "note": "bytes per SURVEY s8(d): 10 B/point read + 10 B/voxel written, over the merge's device time"}}
+    # ---- self-check, frame 0: this rank's voxels against the CPU oracle of the same inputs
+    check = "skipped"
+    if not args.no_check:
+        import oracle
+        R = oracle.restatement()
+        recs = []
+        for cam in range(cams):
+            recs.append(oracle_records("baseline", cam, synth.depth_frame(w, h, cam, 0), synth.color_frame(w, h, cam, 0), w, h))
+        got_st = stitched[0].payload.cpu().numpy().view(np.int16).reshape(-1, 5)
+        ok = np.array_equal(got_st, np.concatenate(recs))
+        t0 = time.perf_counter()
+        want_vox = R.voxel_merge(np.concatenate(recs), LEAF_MM)
+        t_vox = time.perf_counter() - t0
+        if world == 1:
+            got = outs[0][: nv[0] * 5].cpu().numpy().reshape(-1, 5)
+            ok = ok and nv[0] == len(want_vox) and np.array_equal(got, want_vox)
+        else:
+            splits, _ = ctx.voxel_slab_plan_dev(stitched[0].payload.data_ptr(), n, LEAF_MM, world, cs)
+            kz = np.floor_divide(want_vox[:, 2].astype(np.int32), LEAF_MM)
+            sel = want_vox[(kz >= splits[rank]) & (kz < splits[rank + 1])]
+            got = outs[0][: nv[0] * 5].cpu().numpy().reshape(-1, 5)
+            ok = ok and nv[0] == len(sel) and np.array_equal(got, sel)
+        flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        check = "ok" if flag.item() == 1.0 else "MISMATCH"
+        if rank == 0 and not args.no_cpu and world == 1:
+            # CPU baseline on the same frame: the reference's concat loop (sendStitchToUnity, compiled from
+            # src/pcs-multicamera-client.cpp when oracle/_ref is present) + the oracle's voxel merge (the
+            # reference has no voxel grid of its own, SURVEY F1), one thread as in the reference's stitcher
+            t0 = time.perf_counter()
+            R.concat([r.reshape(-1) for r in recs], 1)
+            t_cat = time.perf_counter() - t0
+            res["cpu_baseline"] = {"value": n / (t_cat + t_vox) / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "port",
+                                   "sample": "1 stitched frame (%d points): concat loop of sendStitchToUnity "
+                                             "(src/pcs-multicamera-client.cpp:385-392, restated) %.1f ms + oracle voxel merge "
+                                             "(qsort, own spec) %.1f ms" % (n, t_cat * 1e3, t_vox * 1e3)}
+    res["check"] = check
+    for b in batches:
+        b.close()
+    ctx.close()
+    return res
 
 
 # ------------------------------------------------------------------------------------
@@ -207,7 +453,7 @@ def main():
     import torch.distributed as dist
 
     import pointcloud_stitching_b200 as pcs
-    from pointcloud_stitching_b200 import synth
+    from pointcloud_stitching_b200 import multigpu, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -218,35 +464,37 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    timer = Timer(torch, dist, world)
     S, F = args.streams, args.frames
-    trans = synth.D2C_BASELINE if args.tex == "baseline" else (0.0, 0.0, 0.0)
+    cal = tex_calibration(args.tex)
+    cw, ch = cal["cw"], cal["ch"]
+    descs = stream_descs(pcs, synth, args.tex, world * S)
 
     # ABI streams S..2S-1 mirror 0..S-1: the e2e leg double-buffers every camera (two frames in flight)
     ctx = pcs.Context(device=local, max_streams=2 * S, kernel_variant=args.variant)
     for s in range(S):
-        cam = rank * S + s
         for k in (s, S + s):
-            ctx.set_stream(k, pcs.stream_desc(W, H, tf=synth.TF_STITCH[cam % 8], translation=trans))
+            ctx.set_stream(k, descs[rank * S + s])
 
-    d_np, c_np = make_frames(S, F, rank)
+    d_np, c_np = make_frames(S, F, rank, cw, ch)
     d_dev = torch.from_numpy(d_np.view(np.int16)).cuda()
     c_dev = torch.from_numpy(c_np).cuda()
     # stitched buffers, one per frame index: [pad 12][int32 bytes][world x S cameras x records]
-    from pointcloud_stitching_b200 import multigpu
     slot = S * NPTS * 10
     layout = multigpu.StitchLayout([NPTS] * (world * S), world)
     exchange = "none" if world == 1 else args.exchange
-    sset = fset = None
+    sset = fset = pctx = None
     if exchange == "pull":
         try:
-            fset = multigpu.SymmetricFrameSet(layout, rank, torch.device("cuda", local), W, H, F)
+            fset = multigpu.SymmetricFrameSet(layout, rank, torch.device("cuda", local), W, H, F, stride=cw * 3,
+                                              color_height=ch)
             for s in range(S):
                 for f in range(F):
                     fset.upload(rank * S + s, f, d_np[s, f], c_np[s, f])
             # every rank computes every camera: one context whose stream ids are the camera indices
             pctx = pcs.Context(device=local, max_streams=world * S, kernel_variant=args.variant)
             for cam in range(world * S):
-                pctx.set_stream(cam, pcs.stream_desc(W, H, tf=synth.TF_STITCH[cam % 8], translation=trans))
+                pctx.set_stream(cam, descs[cam])
         except Exception as e:
             if rank == 0:
                 print("bench: symmetric memory unavailable (%r); falling back to --exchange nccl" % (e,), file=sys.stderr)
@@ -300,19 +548,15 @@ def main():
                 dist.all_gather_into_tensor(rec_views[f], rec_views[f][rank * slot:(rank + 1) * slot])
         cs.wait_stream(comm)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    barrier = timer.barrier
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     # A step is ~0.2 ms, so the timed region is a few milliseconds, shorter than nvidia-smi's
     # sampling period: keep the GPU busy with the same work for ~0.15 s first (a couple of clock
     # samples under this very load), then time K steps back to back; the sampler runs across both.
-    # (A much longer ramp -- 0.5 s -- runs this 1 kW part into sw_power_cap at ~1870 MHz, -8 %.)
+    # (A much longer ramp runs this 1 kW part into sw_power_cap at ~1870 MHz: that is the "sustained"
+    # figure reported beside this burst figure.)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -336,6 +580,35 @@ def main():
     pts_step = world * S * F * NPTS
     value = pts_step / (ms_step * 1e-3) / 1e6
 
+    # ---- the stitched bytes of this run, verified on every rank -------------------------------------
+    stitched_check = "skipped"
+    if not args.no_check:
+        ok = True
+        # (a) frame 0 of one camera per rank (own cameras AND pulled / received peers' cameras) against a K1-local
+        #     recompute from regenerated inputs; (b) on rank 0 one peer camera against the CPU oracle
+        cams_to_check = sorted({r * S for r in range(world)} | {rank * S + S - 1})
+        cctx = pcs.Context(device=local, max_streams=1, kernel_variant=args.variant)
+        for cam in cams_to_check:
+            z, col = synth.depth_frame(W, H, cam, 0), synth.color_frame(cw, ch, cam, 0)
+            cctx.set_stream(0, descs[cam])
+            dz, dc = torch.from_numpy(z.view(np.int16)).cuda(), torch.from_numpy(col).cuda()
+            pay = torch.zeros(NPTS * 10, dtype=torch.uint8, device="cuda")
+            b = cctx.batch([(0, dz.data_ptr(), dc.data_ptr(), pay.data_ptr())])
+            b.run(cs.cuda_stream)
+            torch.cuda.synchronize()
+            ok = ok and bool(torch.equal(pay, stitched[0].slot(cam)))
+            b.close()
+            if rank == 0 and cam == cams_to_check[-1 if world > 1 else 0]:
+                want = oracle_records(args.tex, cam, z, col)
+                ok = ok and np.array_equal(pay.cpu().numpy().view(np.int16).reshape(-1, 5), want)
+        hdr = int(np.frombuffer(stitched[0].wire_bytes()[:4].cpu().numpy().tobytes(), np.int32)[0])
+        ok = ok and hdr == world * S * NPTS * 10
+        cctx.close()
+        flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        stitched_check = "ok" if flag.item() == 1.0 else "MISMATCH"
+
     # kernel-only timing of K1 without any exchange (for N > 1 the step above also moves the
     # records over NVLink); this is what the HBM roofline refers to
     local_batches = batches if world == 1 else [ctx.batch(all_jobs)]
@@ -355,103 +628,148 @@ def main():
     # one k1_pipe launch there); for N > 1 the step also holds the exchange, so the K1-only loop
     launch_ms = (ms_step if world == 1 else ms_kernel_step) / launches_per_step_local
     peak, peak_src = measured_peak()
-    alg_bytes_launch = ALG_BYTES_PER_POINT * S * F * NPTS / launches_per_step_local
+    color_bytes = ch * cw * 3 / NPTS          # colour bytes per depth pixel (3 when the frames have the same size)
+    alg_bpp = 2 + color_bytes + 10
+    alg_bytes_launch = alg_bpp * S * F * NPTS / launches_per_step_local
     achieved = alg_bytes_launch / (launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic("k1") if args.tex == "baseline" else (None, None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "k1_pipe" if args.variant != 1 else "k1_direct",
-                "algorithmic_bytes_per_launch": alg_bytes_launch, "launch_ms": launch_ms}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": "k1_pipe" if args.variant != 1 else "k1_direct",
+                "algorithmic_bytes_per_point": alg_bpp, "algorithmic_bytes_per_launch": alg_bytes_launch, "launch_ms": launch_ms}
+
+    # ---- sustained: the same K1 step back to back for >= 2 s (power-capped clocks), beside the burst figure
+    sustained = None
+    if args.sustained_seconds > 0:
+        sam2 = ClockSampler(local)
+        if rank == 0:
+            sam2.start()
+        n_sus = max(args.steps, int(args.sustained_seconds / (ms_kernel_step * 1e-3)) + 1)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(cs)
+        for _ in range(n_sus):
+            for b in local_batches:
+                b.run(cs.cuda_stream)
+        s1.record(cs)
+        torch.cuda.synchronize()
+        sus_ms = s0.elapsed_time(s1)
+        sus_clocks = sam2.stop() if rank == 0 else None
+        sus_ach = alg_bpp * S * F * NPTS * n_sus / (sus_ms * 1e-3) / 1e9
+        sustained = {"seconds": sus_ms * 1e-3, "steps": n_sus, "value": S * F * NPTS * n_sus / (sus_ms * 1e-3) / 1e6,
+                     "unit": "Mpoints/s per GPU (K1 only, no exchange)", "achieved": sus_ach, "frac": sus_ach / peak,
+                     "clocks": sus_clocks}
 
     # ---- end to end through the reference-facing C-ABI call, host buffers -------------
     e2e = None
     if not args.no_e2e:
-        hz = [[ctx.host_alloc(NPTS * 2, np.uint16) for _ in range(F)] for _ in range(S)]
-        hc = [[ctx.host_alloc(NPTS * 3, np.uint8) for _ in range(F)] for _ in range(S)]
-        hb = [[ctx.new_camera_buffer(pinned=True) for _ in range(S)] for _ in range(2)]
-        for s in range(S):
-            for f in range(F):
-                hz[s][f][:] = d_np[s, f].reshape(-1)
-                hc[s][f][:] = c_np[s, f].reshape(-1)
-
-        def e2e_step():
-            total = 0
-            if args.e2e_depth == 1:
-                for f in range(F):
-                    for s in range(S):
-                        ctx.send_begin(s, hz[s][f], hc[s][f], hb[0][s], True)
-                    for s in range(S):
-                        total += ctx.send_end(s)
-                return total
-            # software pipeline: frame f of every camera is in flight while frame f-1 drains
-            for f in range(F):
-                slot = f & 1
-                if f >= 2:
-                    for s in range(S):
-                        total += ctx.send_end(slot * S + s)
-                for s in range(S):
-                    ctx.send_begin(slot * S + s, hz[s][f], hc[s][f], hb[slot][s], True)
-            for f in range(max(0, F - 2), F):
-                for s in range(S):
-                    total += ctx.send_end((f & 1) * S + s)
-            return total
-
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        n_e2e = max(3, min(args.steps, 10))
-        for _ in range(n_e2e):
-            got = e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        assert got == S * F * NPTS * 10
-        if world > 1:
-            t = torch.tensor([dt], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * S * F * NPTS * n_e2e / dt / 1e6, "unit": "Mpoints/s",
-               "h2d_bytes_per_step": S * F * NPTS * 5, "d2h_bytes_per_step": S * F * NPTS * 10,
-               "api": "pcs_b200_send_xyzrgb_begin/_end (host z16+RGB8 in, reference camera buffer out), "
-                      "%d cameras x %d frame(s) in flight, pinned host buffers" % (S, args.e2e_depth), "steps": n_e2e}
+        e2e = run_e2e(args, torch, dist, pcs, synth, ctx, descs, d_np, c_np, rank, world, local, timer)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_reference(os.cpu_count() or 1, 40, args.tex)
-        cpu1 = cpu_reference(1, 20, args.tex)
+        cpu = cpu_reference(os.cpu_count() or 1, 40, args.tex, d_np, c_np)
+        cpu1 = cpu_reference(1, 12, args.tex, d_np, c_np)
         cpu["single_thread_mpoints_s"] = cpu1["value"]
         cpu["single_thread_pack_only_mpoints_s"] = cpu1["pack_only_mpoints_s"]
 
+    # ---- BASELINE configs #3 and #5 into the same line ------------------------------------------------
+    configs = {}
+    want = [] if args.configs in ("none", "") else [c.strip() for c in args.configs.split(",")]
+    for name in want:
+        try:
+            r = bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, world, local, timer, peak)
+        except Exception as e:  # a failing extra config must not lose the headline; it is reported as failed
+            r = {"error": repr(e), "check": "ERROR"}
+        if r is not None:
+            configs[name] = r
+
     link_div = 2 if exchange == "pull" else 1
+    bad = stitched_check == "MISMATCH" or any(c.get("check") in ("MISMATCH", "ERROR") for c in configs.values())
     if rank == 0:
+        nvlink = None
+        if world > 1:
+            gbps = (world - 1) * slot * F / link_div / (ms_step * 1e-3) / 1e9
+            nvlink = {"recv_bytes_per_gpu_per_step": (world - 1) * slot * F // link_div, "recv_GBps_per_gpu": gbps,
+                      "peer_copy_peak_GBps": 770.0, "frac_of_peer_copy_peak": gbps / 770.0,
+                      "note": "every GPU must take in (N-1)/N of the stitched cloud -- as 10 B/pt records (fused, nccl) or as "
+                              "5 B/pt raw frames it deprojects itself (pull): this link rate, not HBM, bounds N > 1 "
+                              "(B200_PROFILING.md: 770 GB/s measured peer copy per direction)"}
         line = {
             "metric": METRIC, "value": value, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%d streams/GPU x %d frames x 1280x720 z16 depth + RGB8, fused deproject+transform+"
-                                   "colour+pack (K1)%s; depth->colour extrinsics: %s" % (
-                                       S, F, "" if world == 1 else {
-                                           "pull": " on every rank over ALL cameras' frames: the peers' raw z16+RGB8 tiles are the "
-                                                   "kernel's own TMA loads from NVLink peer memory (all-gather fused into the "
-                                                   "compute kernel's input pipeline, 5 B/pt on the link)",
-                                           "fused": " + all-gather of the packed records fused into the kernel (peer TMA stores "
-                                                    "over NVLink, 10 B/pt on the link)",
-                                           "nccl": " + in-place NCCL all-gather of the packed records"}[exchange],
-                                       "15 mm baseline" if args.tex == "baseline" else "identity"),
-                       "streams_per_gpu": S, "frames_per_step": F, "points_per_step": pts_step,
-                       "l2": "working set %.0f MB per step per GPU >> 126 MB L2 (no flush needed)" % (
-                           ALG_BYTES_PER_POINT * S * F * NPTS / 1e6),
-                       "kernel_variant": args.variant, "tex": args.tex, "exchange": exchange},
+            "config": headline_config(args, world),
+            "impl_detail": {"kernel_variant": args.variant, "exchange": exchange, "exchange_note": {
+                "none": "single GPU: K1 writes every camera's slot of the stitched buffer in place",
+                "pull": "K1 on every rank over ALL cameras' frames: the peers' raw z16+RGB8 tiles are the kernel's own TMA "
+                        "loads from NVLink peer memory (all-gather fused into the compute kernel's input pipeline, 5 B/pt)",
+                "fused": "all-gather of the packed records fused into K1 (peer TMA stores over NVLink, 10 B/pt)",
+                "nccl": "K1 then in-place NCCL all-gather of the packed records"}[exchange]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "sustained": sustained, "cpu_baseline": cpu, "stitched_check": stitched_check,
             "kernel_only": {"ms_per_step": ms_kernel_step, "mpoints_s_per_gpu": S * F * NPTS / (ms_kernel_step * 1e-3) / 1e6},
-            "nvlink": None if world == 1 else {
-                "recv_bytes_per_gpu_per_step": (world - 1) * slot * F // link_div,
-                "recv_GBps_per_gpu": (world - 1) * slot * F / link_div / (ms_step * 1e-3) / 1e9,
-                "note": "every GPU must take in (N-1)/N of the stitched cloud -- as 10 B/pt records (fused, nccl) or as "
-                        "5 B/pt raw frames it deprojects itself (pull): this link rate, not HBM, bounds N > 1 "
-                        "(B200_PROFILING.md: 770 GB/s measured peer copy per direction)"},
+            "nvlink": nvlink, "configs": configs,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if bad:
+        sys.exit("bench.py: output verification FAILED (stitched_check=%s, configs=%s)" % (
+            stitched_check, {k: v.get("check") for k, v in configs.items()}))
+
+
+def run_e2e(args, torch, dist, pcs, synth, ctx, descs, d_np, c_np, rank, world, local, timer):
+    """The same metric through the reference-facing C ABI with host buffers: pinned z16 + RGB8 in, the
+    reference's camera buffers out, host<->device copies inside the timed region."""
+    S, F = args.streams, args.frames
+    ch, cwb = c_np.shape[2], c_np.shape[3]
+    hz = [[ctx.host_alloc(NPTS * 2, np.uint16) for _ in range(F)] for _ in range(S)]
+    hc = [[ctx.host_alloc(ch * cwb, np.uint8) for _ in range(F)] for _ in range(S)]
+    hb = [[ctx.new_camera_buffer(pinned=True) for _ in range(S)] for _ in range(2)]
+    for s in range(S):
+        for f in range(F):
+            hz[s][f][:] = d_np[s, f].reshape(-1)
+            hc[s][f][:] = c_np[s, f].reshape(-1)
+
+    def e2e_step():
+        total = 0
+        if args.e2e_depth == 1:
+            for f in range(F):
+                for s in range(S):
+                    ctx.send_begin(s, hz[s][f], hc[s][f], hb[0][s], True)
+                for s in range(S):
+                    total += ctx.send_end(s)
+            return total
+        # software pipeline: frame f of every camera is in flight while frame f-1 drains
+        for f in range(F):
+            slot = f & 1
+            if f >= 2:
+                for s in range(S):
+                    total += ctx.send_end(slot * S + s)
+            for s in range(S):
+                ctx.send_begin(slot * S + s, hz[s][f], hc[s][f], hb[slot][s], True)
+        for f in range(max(0, F - 2), F):
+            for s in range(S):
+                total += ctx.send_end((f & 1) * S + s)
+        return total
+
+    e2e_step()
+    timer.barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(3, min(args.steps, 10))
+    for _ in range(n_e2e):
+        got = e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert got == S * F * NPTS * 10
+    if world > 1:
+        t = torch.tensor([dt], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return {"value": world * S * F * NPTS * n_e2e / dt / 1e6, "unit": "Mpoints/s",
+            "h2d_bytes_per_step": S * F * (NPTS * 2 + ch * cwb), "d2h_bytes_per_step": S * F * NPTS * 10,
+            "api": "pcs_b200_send_xyzrgb_begin/_end (host z16+RGB8 in, reference camera buffer out), "
+                   "%d cameras x %d frame(s) in flight, pinned host buffers" % (S, args.e2e_depth), "steps": n_e2e}
 
 
 if __name__ == "__main__":

@@ -14,7 +14,8 @@
  *                           (src/pcs-multicamera-client.cpp:378,385-395)
  *
  * Plain C types only; no torch / CUDA types in any signature (CUDA streams are
- * passed as void*).  Every function returns >= 0 on success (a count or a byte
+ * passed as void*).  Every call runs on the context's device and restores the calling
+ * thread's current CUDA device before it returns.  Every function returns >= 0 on success (a count or a byte
  * size, as the reference function does) and a negative pcs_status on failure;
  * nothing here ever calls exit().  There is NO CPU fallback: without a CUDA
  * device pcs_b200_create() fails with PCS_ERR_CUDA.
@@ -111,7 +112,10 @@ PCS_API void pcs_b200_destroy(pcs_ctx *ctx);
 PCS_API const char *pcs_b200_last_error(const pcs_ctx *ctx);
 
 /* Replaces the globals behind `initialized` (src/pcs-camera-optimized.cpp:349-409)
- * and the hard-coded transform (:64-72).  May be called again at any time. */
+ * and the hard-coded transform (:64-72).  May be called again at any time for the host-buffer
+ * calls.  A batch (pcs_b200_batch_create) freezes its streams' geometry, calibration and cutoff
+ * settings: under a live batch only `tf` may change; after any other change pcs_b200_batch_run
+ * returns PCS_ERR_INVALID until the batch is destroyed and created again. */
 PCS_API int pcs_b200_set_stream(pcs_ctx *ctx, int stream, const pcs_stream_desc *desc);
 
 /* ---- camera side, host buffers (what the reference's main() calls) ---------- */
@@ -174,7 +178,10 @@ PCS_API int pcs_b200_batch_launches(const pcs_batch *batch);
  * GPU each map peer memory with CUDA IPC / symmetric memory instead. */
 PCS_API int pcs_b200_enable_peer(pcs_ctx *ctx, int peer_device);
 
-/* Device-pointer form of pcs_b200_pack_from_vertices. */
+/* Device-pointer form of pcs_b200_pack_from_vertices; asynchronous on cuda_stream.  Without cutoff
+ * the return value is the record count (n).  With cutoff (-c) the count is only known on the
+ * device: it is written to *count_dev (required then, PCS_ERR_INVALID if NULL) and the return value
+ * is the UPPER BOUND n -- records beyond *count_dev in payload_dev are stale. */
 PCS_API int pcs_b200_pack_from_vertices_dev(pcs_ctx *ctx, int stream, const float *xyz_dev,
                                     const float *uv_dev, int n, const uint8_t *color_dev,
                                     int16_t *payload_dev, int32_t *count_dev, void *cuda_stream);

@@ -2,9 +2,11 @@
 
 The product is ``libpcs_b200.so`` (hand-written sm_100a CUDA behind the C ABI of
 ``include/pcs_b200.h``).  This module is the thin ctypes binding used by the
-tests and by ``bench.py``; it holds no compute and has no CPU fallback: if the
-library is missing the import fails, and without a CUDA device ``Context()``
-raises.
+tests and by ``bench.py``; it holds no compute and has no CPU fallback: the
+library is opened on first use of ``lib`` (so that ``synth`` / ``calibration`` can
+be imported by processes that must not map the product, e.g. the CPU reference arm
+of ``bench.py``); if it is missing that first use raises ImportError, and without a
+CUDA device ``Context()`` raises.
 """
 from __future__ import annotations
 
@@ -141,7 +143,24 @@ def _load():
     return lib
 
 
-lib = _load()
+class _LazyLib:
+    """dlopens libpcs_b200.so on first attribute access (never at import of the package)."""
+
+    _real = None
+
+    def __getattr__(self, name):
+        real = object.__getattribute__(self, "_real")
+        if real is None:
+            real = _load()
+            object.__setattr__(self, "_real", real)
+        return getattr(real, name)
+
+    @property
+    def loaded(self):
+        return object.__getattribute__(self, "_real") is not None
+
+
+lib = _LazyLib()
 
 
 def _np_ptr(a):

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "pcs_kernels.cuh"
@@ -27,6 +28,7 @@ thread_local std::string g_tls_error;
 
 struct StreamState {
     bool configured = false;
+    unsigned geom_gen = 0;          // bumped whenever anything but `tf` changes (live batches freeze the rest)
     pcs_stream_desc desc{};
     StreamParams params{};
     cudaStream_t cs = nullptr;
@@ -88,6 +90,7 @@ struct pcs_batch {
     std::vector<Group> groups;
     struct CutJob { int job, n, lane_rev, n_tiles; int32_t *d_tiles; };
     std::vector<CutJob> cuts;
+    std::vector<std::pair<int, unsigned>> gens;   // (stream, geom_gen) captured at create
     std::vector<void *> owned;          // scratch to free
     int launches = 0;
     PipeBatch pipe;                     // pipelined-kernel work list (variant 2)
@@ -109,6 +112,22 @@ int fail(pcs_ctx *ctx, int status, const char *fmt, ...) {
     }
     return status;
 }
+
+// Every entry point runs on the context's device and puts the caller's current device back on
+// return (single-process multi-GPU hosts and torch callers keep their own notion of "current").
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != device) changed = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (changed && prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
 
 #define CU(ctx, call)                                                                         \
     do {                                                                                      \
@@ -262,8 +281,16 @@ const char *pcs_b200_status_string(int status) {
     }
 }
 
+// The returned pointer is a per-thread copy: other threads failing on the same context rewrite
+// ctx->error under its lock, never the buffer handed out here.
 const char *pcs_b200_last_error(const pcs_ctx *ctx) {
-    return ctx ? ctx->error.c_str() : g_tls_error.c_str();
+    thread_local std::string copy;
+    if (!ctx) return g_tls_error.c_str();
+    {
+        std::lock_guard<std::mutex> lk(const_cast<pcs_ctx *>(ctx)->mu);
+        copy = ctx->error;
+    }
+    return copy.c_str();
 }
 
 int pcs_b200_create(const pcs_config *cfg, pcs_ctx **out) {
@@ -278,7 +305,7 @@ int pcs_b200_create(const pcs_config *cfg, pcs_ctx **out) {
     }
     if (cfg->device < 0 || cfg->device >= ndev)
         return fail(nullptr, PCS_ERR_INVALID, "device %d out of range", cfg->device);
-    CU(nullptr, cudaSetDevice(cfg->device));
+    DeviceGuard dg_(cfg->device);
     cudaDeviceProp prop;
     CU(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10)
@@ -314,7 +341,7 @@ int pcs_b200_create(const pcs_config *cfg, pcs_ctx **out) {
 
 void pcs_b200_destroy(pcs_ctx *ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard dg_(ctx->device);
     for (int i = 0; ctx->streams && i < ctx->max_streams; ++i) {
         StreamState &s = ctx->streams[i];
         if (s.cs) { cudaStreamSynchronize(s.cs); cudaStreamDestroy(s.cs); }
@@ -343,9 +370,17 @@ int pcs_b200_set_stream(pcs_ctx *ctx, int stream, const pcs_stream_desc *desc) {
     if (d.depth.width < 0 || d.depth.height < 0 ||
         (long long)d.depth.width * d.depth.height > (1ll << 28))
         return fail(ctx, PCS_ERR_INVALID, "bad depth geometry");
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     StreamState &s = ctx->streams[stream];
     std::lock_guard<std::mutex> lk(s.mu);
+    if (s.configured) {
+        // a live batch froze grid sizes, -c scratch and the pipelined kernel's calibration: only the
+        // camera -> world transform may change under it
+        pcs_stream_desc a = s.desc, b = d;
+        memset(a.tf, 0, sizeof a.tf);
+        memset(b.tf, 0, sizeof b.tf);
+        if (memcmp(&a, &b, sizeof a) != 0) ++s.geom_gen;
+    }
     s.desc = d;
     digest(d, s.params);
     s.configured = true;
@@ -355,7 +390,7 @@ int pcs_b200_set_stream(pcs_ctx *ctx, int stream, const pcs_stream_desc *desc) {
 
 void *pcs_b200_host_alloc(pcs_ctx *ctx, size_t bytes) {
     void *p = nullptr;
-    if (ctx) cudaSetDevice(ctx->device);
+    DeviceGuard dg_(ctx ? ctx->device : 0);
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
         cudaGetLastError();
         fail(ctx, PCS_ERR_NOMEM, "cudaHostAlloc of %zu bytes failed", bytes);
@@ -365,13 +400,13 @@ void *pcs_b200_host_alloc(pcs_ctx *ctx, size_t bytes) {
 }
 
 void pcs_b200_host_free(pcs_ctx *ctx, void *p) {
-    if (ctx) cudaSetDevice(ctx->device);
+    DeviceGuard dg_(ctx ? ctx->device : 0);
     if (p) cudaFreeHost(p);
 }
 
 int pcs_b200_synchronize(pcs_ctx *ctx, void *cuda_stream) {
     if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     CU(ctx, cudaStreamSynchronize((cudaStream_t)cuda_stream));
     return PCS_OK;
 }
@@ -388,7 +423,7 @@ int pcs_b200_send_xyzrgb_begin(pcs_ctx *ctx, int stream, const uint16_t *z16_hos
     const StreamParams &p = s.params;
     if ((size_t)p.N * 10 + 4 > (size_t)PCS_B200_CAMERA_BUF_SHORTS * 2)
         return fail(ctx, PCS_ERR_CAPACITY, "%d points do not fit the reference's 10 MB camera buffer", p.N);
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     if ((rc = ensure_frame_buffers(ctx, s))) return rc;
     DevJob job{};
     job.z16 = s.d_z16; job.color = s.d_color; job.payload = s.d_payload; job.xyzrgb = nullptr;
@@ -422,7 +457,7 @@ int pcs_b200_send_xyzrgb_end(pcs_ctx *ctx, int stream) {
     std::lock_guard<std::mutex> lk(s.mu);
     if (!s.pending) return fail(ctx, PCS_ERR_INVALID, "stream %d has no frame in flight", stream);
     s.pending = false;
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     CU(ctx, cudaStreamSynchronize(s.cs));
     const StreamParams &p = s.params;
     const int count = p.cutoff ? *s.h_count : p.N;
@@ -461,7 +496,7 @@ int pcs_b200_pack_from_vertices_dev(pcs_ctx *ctx, int stream, const float *xyz_d
         return fail(ctx, PCS_ERR_INVALID, "colour frame must be 4-byte aligned");
     StreamState &s = ctx->streams[stream];
     cudaStream_t cs = (cudaStream_t)cuda_stream;
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     const int blocks = (n / 4 + K1A_THREADS - 1) / K1A_THREADS;
     if (!s.params.cutoff) {
         k1a_vertices<false><<<blocks, K1A_THREADS, 0, cs>>>(xyz_dev, uv_dev, n, color_dev, ctx->d_params,
@@ -469,6 +504,10 @@ int pcs_b200_pack_from_vertices_dev(pcs_ctx *ctx, int stream, const float *xyz_d
         CU(ctx, cudaGetLastError());
         return n;
     }
+    // -c: the record count only exists on the device after the compaction; the caller must say where
+    // it goes (the return value below is the upper bound n, not the count)
+    if (!count_dev)
+        return fail(ctx, PCS_ERR_INVALID, "stream %d has cutoff set: count_dev must not be NULL", stream);
     // -c needs scratch: ctx-owned, sized for n
     std::lock_guard<std::mutex> lk(s.mu);
     if ((size_t)n > s.cap_cut) {
@@ -477,14 +516,6 @@ int pcs_b200_pack_from_vertices_dev(pcs_ctx *ctx, int stream, const float *xyz_d
         if ((rc = grow(ctx, s.d_ckeep, (size_t)n))) return rc;
         if ((rc = grow(ctx, s.d_ctiles, (size_t)n / CMP_TILE + 2))) return rc;
         s.cap_cut = n;
-    }
-    if (!count_dev) {
-        if (!s.d_count) {
-            CU(ctx, cudaMalloc(&s.d_count, 64));
-            CU(ctx, cudaHostAlloc(&s.h_count, 64, cudaHostAllocDefault));
-            CU(ctx, cudaMalloc(&s.d_job, sizeof(DevJob)));
-        }
-        count_dev = s.d_count;
     }
     k1a_vertices<true><<<blocks, K1A_THREADS, 0, cs>>>(xyz_dev, uv_dev, n, color_dev, ctx->d_params, stream,
                                                s.d_cdense, s.d_ckeep);
@@ -504,7 +535,7 @@ int pcs_b200_pack_from_vertices(pcs_ctx *ctx, int stream, const float *xyz_host,
     if (n == 0) return 0;
     if (!xyz_host || !uv_host || !color_host || !payload_host) return fail(ctx, PCS_ERR_INVALID, "null buffer");
     StreamState &s = ctx->streams[stream];
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     const size_t cb = (size_t)s.params.CH * s.params.stride;
     {
         std::lock_guard<std::mutex> lk(s.mu);
@@ -549,7 +580,7 @@ static int batch_create_impl(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs
     if (!ctx || !jobs || !out || n_jobs < 1 || n_jobs > 65535)
         return fail(ctx, PCS_ERR_INVALID, "bad batch arguments (1 <= n_jobs <= 65535)");
     *out = nullptr;
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     pcs_batch *b = new pcs_batch;
     auto bail = [&](int rc) { pcs_b200_batch_destroy(ctx, b); return rc; };
     // order jobs by kernel variant so that each variant is one launch
@@ -596,6 +627,7 @@ static int batch_create_impl(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs
             b->cuts.push_back({(int)b->jobs.size(), p.N, p.lane_rev, n_tiles, (int32_t *)tiles});
         }
         b->jobs.push_back(d);
+        b->gens.emplace_back(in.stream, ctx->streams[in.stream].geom_gen);
     }
     if (cudaMalloc(&b->d_jobs, sizeof(DevJob) * b->jobs.size()) != cudaSuccess) {
         cudaGetLastError();
@@ -668,7 +700,7 @@ int pcs_b200_batch_create_fanout(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_
 int pcs_b200_enable_peer(pcs_ctx *ctx, int peer_device) {
     if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
     if (peer_device == ctx->device) return PCS_OK;
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     int can = 0;
     CU(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
     if (!can) return fail(ctx, PCS_ERR_UNSUPPORTED, "device %d cannot access device %d", ctx->device, peer_device);
@@ -684,7 +716,12 @@ int pcs_b200_enable_peer(pcs_ctx *ctx, int peer_device) {
 int pcs_b200_batch_run(pcs_ctx *ctx, pcs_batch *b, void *cuda_stream) {
     if (!ctx || !b) return fail(ctx, PCS_ERR_INVALID, "null argument");
     cudaStream_t cs = (cudaStream_t)cuda_stream;
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
+    for (const auto &sg : b->gens)
+        if (ctx->streams[sg.first].geom_gen != sg.second)
+            return fail(ctx, PCS_ERR_INVALID,
+                        "stream %d was reconfigured after this batch was created (only tf may change under a live "
+                        "batch): destroy the batch and create it again", sg.first);
     if (b->use_pipe) {
         pipe_launch(b->pipe, b->d_jobs, ctx->d_params, cs);
         CU(ctx, cudaGetLastError());
@@ -708,7 +745,7 @@ int pcs_b200_batch_launches(const pcs_batch *b) { return b ? b->launches : 0; }
 
 void pcs_b200_batch_destroy(pcs_ctx *ctx, pcs_batch *b) {
     if (!b) return;
-    if (ctx) cudaSetDevice(ctx->device);
+    DeviceGuard dg_(ctx ? ctx->device : 0);
     for (void *p : b->owned) cudaFree(p);
     cudaFree(b->d_jobs);
     pipe_free(b->pipe);
@@ -748,7 +785,7 @@ static int stitch_common(pcs_ctx *ctx, const int16_t *const *payload_dev, const 
     if (total * 10 > 0x7fffffffll) return fail(ctx, PCS_ERR_CAPACITY, "stitched payload exceeds int32");
     tab.out_off[n_cams] = (int)total;
     if ((size_t)total * 10 + 4 > cap) return fail(ctx, PCS_ERR_CAPACITY, "stitched buffer too small: need %lld bytes", total * 10 + 4);
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     // vectorised path: no decimation, whole octets per camera, 16-byte aligned everywhere, and
     // (PCL) coordinates that stay far inside int32 so that cvt.rzi == x86 cvttss2si
     bool vec = downsample == 1 && !cloud32_dev && total > 0 &&
@@ -800,7 +837,7 @@ static int stitch_host(pcs_ctx *ctx, const int16_t *const *payload_host, const i
     if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
     if (!payload_host || !n_shorts || !stitched_host || n_cams < 0 || n_cams > MAX_CAMS)
         return fail(ctx, PCS_ERR_INVALID, "bad stitch arguments");
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->scratch_mu);
     size_t in_bytes = 0;
     std::vector<size_t> off(n_cams);
@@ -875,7 +912,7 @@ int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, in
     int rc = voxel_args_ok(ctx, records_dev, n, leaf_mm, out_dev);
     if (rc) return rc;
     if (n == 0) return 0;
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->scratch_mu);
     // voxel_variant: 0 = one-sweep sort when the (key, index) word fits 64 bits, else the pair sort
     rc = -4;
@@ -894,7 +931,7 @@ int pcs_b200_voxel_slab_plan_dev(pcs_ctx *ctx, const int16_t *records_dev, int n
     int rc = voxel_args_ok(ctx, records_dev, n, leaf_mm, kz_splits);
     if (rc) return rc;
     if (n_slabs < 1 || n_slabs > 1024 || !kz_splits) return fail(ctx, PCS_ERR_INVALID, "1 <= n_slabs <= 1024");
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->scratch_mu);
     rc = voxel_slab_plan(ctx->voxel, records_dev, n, leaf_mm, n_slabs, kz_splits, slab_points,
                          (cudaStream_t)cuda_stream, ctx->sm_count);
@@ -906,7 +943,7 @@ int pcs_b200_voxel_merge_slab_dev(pcs_ctx *ctx, const int16_t *records_dev, int 
     int rc = voxel_args_ok(ctx, records_dev, n, leaf_mm, out_dev);
     if (rc) return rc;
     if (n == 0 || kz_lo >= kz_hi) return 0;
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->scratch_mu);
     if (ctx->voxel_variant == 3)
         rc = voxel_merge_sweep<10, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream,
@@ -922,7 +959,7 @@ int pcs_b200_voxel_merge(pcs_ctx *ctx, const int16_t *records_host, int n, int l
     if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
     if (n < 0 || (n && (!records_host || !out_host))) return fail(ctx, PCS_ERR_INVALID, "bad arguments");
     if (n == 0) return 0;
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     int16_t *d_in = nullptr, *d_out = nullptr;
     if (cudaMalloc(&d_in, (size_t)n * 10 + 64) != cudaSuccess || cudaMalloc(&d_out, (size_t)n * 10 + 64) != cudaSuccess) {
         cudaGetLastError();
@@ -947,7 +984,7 @@ int pcs_b200_cloud_to_ply_rows_dev(pcs_ctx *ctx, const void *cloud32_dev, int n,
     if (n < 0 || (n && (!cloud32_dev || !rows_dev))) return fail(ctx, PCS_ERR_INVALID, "bad PLY arguments");
     if (reinterpret_cast<uintptr_t>(cloud32_dev) & 15) return fail(ctx, PCS_ERR_INVALID, "cloud must be 16-byte aligned");
     if (n == 0) return 0;
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     const int groups = (n + 31) / 32;
     const int grid = std::max(1, std::min((groups + PLY_THREADS / 32 - 1) / (PLY_THREADS / 32), ctx->sm_count * 8));
     ply_rows<<<grid, PLY_THREADS, 0, (cudaStream_t)cuda_stream>>>(reinterpret_cast<const uint4 *>(cloud32_dev), n, rows_dev);
@@ -961,7 +998,7 @@ int pcs_b200_cloud_to_ply_rows_dev(pcs_ctx *ctx, const void *cloud32_dev, int n,
 int pcs_b200_save_ply(pcs_ctx *ctx, const void *cloud32_dev, int n, const char *path) {
     if (!ctx || !path) return fail(ctx, PCS_ERR_INVALID, "null argument");
     if (n < 0 || (n && !cloud32_dev)) return fail(ctx, PCS_ERR_INVALID, "bad PLY arguments");
-    CU(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dg_(ctx->device);
     uint8_t *d_rows = nullptr;
     std::vector<uint8_t> rows((size_t)n * PLY_ROW);
     if (n) {

@@ -102,7 +102,10 @@ class StitchedBuffer:
         else:
             for r in range(L.world):
                 if L.rank_bytes[r]:
-                    dist.broadcast(self.payload[L.rank_offset[r]:L.rank_offset[r] + L.rank_bytes[r]], src=r, group=group)
+                    # `src` is a GLOBAL rank: translate the group-local index for groups other than WORLD
+                    src = dist.get_global_rank(group, r) if group is not None else r
+                    dist.broadcast(self.payload[L.rank_offset[r]:L.rank_offset[r] + L.rank_bytes[r]], src=src,
+                                   group=group)
 
     def wire_bytes(self):
         """``[int32 bytes][records]`` exactly as the reference writes it to the viewer socket."""
@@ -141,12 +144,12 @@ class SymmetricStitchedSet:
         self.handle.barrier()
 
 
-def frame_slots(width, height, stride, cams_per_rank_max, n_frames):
+def frame_slots(width, height, stride, cams_per_rank_max, n_frames, color_height=None):
     """Byte offsets inside one rank's raw-frame allocation (the same on every rank):
     ``depth_off(local_cam, frame)``, ``color_off(local_cam, frame)`` and the total size.  Every frame is
     256-byte aligned (the pipelined kernel needs 16)."""
     dz = (width * height * 2 + 255) & ~255
-    dc = (height * stride + 255) & ~255
+    dc = ((height if color_height is None else color_height) * stride + 255) & ~255
     per_frame = dz + dc
     total = max(1, cams_per_rank_max) * n_frames * per_frame
 
@@ -171,13 +174,15 @@ class SymmetricFrameSet:
     than the link, so recomputing a peer's records is cheaper than receiving them.
     """
 
-    def __init__(self, layout: StitchLayout, rank: int, device, width, height, n_frames, stride=None, group=None):
+    def __init__(self, layout: StitchLayout, rank: int, device, width, height, n_frames, stride=None, group=None,
+                 color_height=None):
         import torch.distributed._symmetric_memory as symm
         self.layout, self.rank, self.n_frames = layout, rank, n_frames
         self.width, self.height = width, height
         self.stride = stride if stride is not None else width * 3
         cmax = max(len(c) for c in layout.cams_of)
-        self.depth_off, self.color_off, self.nbytes = frame_slots(width, height, self.stride, cmax, n_frames)
+        self.depth_off, self.color_off, self.nbytes = frame_slots(width, height, self.stride, cmax, n_frames,
+                                                                  color_height)
         self.raw = symm.empty(self.nbytes, dtype=torch.uint8, device=device)
         self.raw.zero_()
         self.handle = symm.rendezvous(self.raw, group if group is not None else dist.group.WORLD)

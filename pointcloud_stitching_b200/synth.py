@@ -41,6 +41,23 @@ IDENTITY = np.eye(4, dtype=np.float32).reshape(-1)
 D2C_BASELINE = (0.015, 0.0, 0.0)
 
 
+
+
+def rotation_colmajor(rx: float, ry: float, rz: float):
+    """rs2_extrinsics-style rotation (column-major 3x3, float32) from small Euler angles in radians."""
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    rxm = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    rym = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    rzm = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    r = (rzm @ rym @ rxm).astype(np.float32)
+    return tuple(float(v) for v in r.T.reshape(-1))
+
+
+# A factory-calibration-like depth -> colour rotation (a few tenths of a degree about every axis): any real
+# D4xx has one; the reference's recordings are 1280x720 Z16 + 1920x1080 RGB8 (src/pcs-camera-grab-frames.cpp:69-70)
+D2C_ROTATION_SMALL = rotation_colmajor(0.004, -0.003, 0.005)
+
+
 def seed_for(cam: int, frame: int) -> int:
     return 0xC0FFEE ^ (cam << 16) ^ frame
 

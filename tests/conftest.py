@@ -10,14 +10,40 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-# the product library and the oracle are build artefacts (git-ignored): make sure they exist
+# the product library and the oracle are build artefacts (git-ignored): make sure they exist.  A host
+# without nvcc (or make) can still run the suite against prebuilt artefacts that travelled with the tree.
 import __graft_entry__  # noqa: E402
 
-__graft_entry__.build()
+try:
+    __graft_entry__.build()
+except Exception as e:  # noqa: BLE001
+    _built = [os.path.join(ROOT, "pointcloud_stitching_b200", "libpcs_b200.so"),
+              os.path.join(ROOT, "oracle", "_build", "libpcs_oracle.so")]
+    if not all(os.path.exists(p) for p in _built):
+        raise
+    print("conftest: build() failed (%r); using the prebuilt libraries" % (e,), file=sys.stderr)
+
+
+def _cuda_available():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        return False
 
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a CPU-only host skips the gpu-marked tests instead of failing them."""
+    if _cuda_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (run with gpurun)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
 
 
 def load_golden(name):
