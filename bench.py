@@ -61,7 +61,7 @@ def parse():
                          "nccl = K1 then all-gather")
     ap.add_argument("--configs", default="c3,c5", help="extra BASELINE configs measured into the same line ('none' to skip)")
     ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the sustained K1 leg (0 to skip)")
-    ap.add_argument("--e2e-depth", type=int, default=2, choices=[1, 2], help="frames in flight per camera in the e2e leg")
+    ap.add_argument("--e2e-slots", type=int, default=3, choices=[1, 2, 3, 4], help="stitched frames in flight in the e2e leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the stitched-bytes verification")
@@ -685,6 +685,12 @@ def main():
 
     link_div = 2 if exchange == "pull" else 1
     bad = stitched_check == "MISMATCH" or any(c.get("check") in ("MISMATCH", "ERROR") for c in configs.values())
+    e2e_bad = e2e is not None and e2e.get("check") == "MISMATCH"
+    if world > 1:
+        fl = torch.tensor([1.0 if e2e_bad else 0.0], device="cuda")
+        dist.all_reduce(fl, op=dist.ReduceOp.MAX)
+        e2e_bad = fl.item() > 0
+    bad = bad or e2e_bad
     if rank == 0:
         nvlink = None
         if world > 1:
@@ -719,29 +725,39 @@ def main():
 
 
 def run_e2e(args, torch, dist, pcs, synth, ctx, descs, d_np, c_np, rank, world, local, timer):
-    """The same metric through the reference-facing C ABI with host buffers: pinned z16 + RGB8 in, the
-    reference's camera buffers out, host<->device copies inside the timed region."""
+    """The same metric through the reference-facing C ABI with HOST buffers on both sides: pinned z16 + RGB8
+    frames of this GPU's S cameras in, the reference's STITCHED buffer `[int32][cam0 records][cam1 records]...`
+    out (pcs_b200_stitch_frames_begin/_end: H2D per camera, ONE batched k1 launch into the device-resident
+    stitched buffer, one D2H), two frames in flight on two slots; host<->device copies inside the timed region.
+    Beside it: the per-camera call (pcs_b200_send_xyzrgb_begin/_end, S separate camera buffers) and a plain
+    cudaMemcpy probe moving the same bytes (what the PCIe link / host memory allow with no kernel at all)."""
     S, F = args.streams, args.frames
     ch, cwb = c_np.shape[2], c_np.shape[3]
     hz = [[ctx.host_alloc(NPTS * 2, np.uint16) for _ in range(F)] for _ in range(S)]
     hc = [[ctx.host_alloc(ch * cwb, np.uint8) for _ in range(F)] for _ in range(S)]
     hb = [[ctx.new_camera_buffer(pinned=True) for _ in range(S)] for _ in range(2)]
+    NS = args.e2e_slots
+    hs = [ctx.host_alloc(4 + S * NPTS * 10, np.uint8) for _ in range(NS)]
     for s in range(S):
         for f in range(F):
             hz[s][f][:] = d_np[s, f].reshape(-1)
             hc[s][f][:] = c_np[s, f].reshape(-1)
+    cams = list(range(S))
 
-    def e2e_step():
+    def stitched_step():
         total = 0
-        if args.e2e_depth == 1:
-            for f in range(F):
-                for s in range(S):
-                    ctx.send_begin(s, hz[s][f], hc[s][f], hb[0][s], True)
-                for s in range(S):
-                    total += ctx.send_end(s)
-            return total
-        # software pipeline: frame f of every camera is in flight while frame f-1 drains
         for f in range(F):
+            slot = f % NS
+            if f >= NS:
+                total += ctx.stitch_frames_end(slot)
+            ctx.stitch_frames_begin(slot, cams, [hz[s][f] for s in range(S)], [hc[s][f] for s in range(S)], hs[slot])
+        for f in range(max(0, F - NS), F):
+            total += ctx.stitch_frames_end(f % NS)
+        return total
+
+    def camera_step():
+        total = 0
+        for f in range(F):      # software pipeline: frame f of every camera is in flight while frame f-1 drains
             slot = f & 1
             if f >= 2:
                 for s in range(S):
@@ -753,23 +769,70 @@ def run_e2e(args, torch, dist, pcs, synth, ctx, descs, d_np, c_np, rank, world, 
                 total += ctx.send_end((f & 1) * S + s)
         return total
 
-    e2e_step()
-    timer.barrier()
-    t0 = time.perf_counter()
+    # plain copies of the same bytes, same double buffering, no kernel
+    tz = [[torch.from_numpy(hz[s][f].view(np.int16)) for f in range(F)] for s in range(S)]
+    tc = [[torch.from_numpy(hc[s][f]) for f in range(F)] for s in range(S)]
+    ts = [torch.from_numpy(hs[k]) for k in range(NS)]
+    dz = [[torch.empty(NPTS, dtype=torch.int16, device="cuda") for _ in range(S)] for _ in range(NS)]
+    dc = [[torch.empty(ch * cwb, dtype=torch.uint8, device="cuda") for _ in range(S)] for _ in range(NS)]
+    ds = [torch.empty(4 + S * NPTS * 10, dtype=torch.uint8, device="cuda") for _ in range(NS)]
+    streams = [torch.cuda.Stream() for _ in range(NS)]
+
+    def probe_step():
+        for f in range(F):
+            k = f % NS
+            with torch.cuda.stream(streams[k]):
+                for s in range(S):
+                    dz[k][s].copy_(tz[s][f], non_blocking=True)
+                    dc[k][s].copy_(tc[s][f], non_blocking=True)
+                ts[k].copy_(ds[k], non_blocking=True)
+        for st in streams:
+            st.synchronize()
+        return S * F * NPTS * 10
+
     n_e2e = max(3, min(args.steps, 10))
-    for _ in range(n_e2e):
-        got = e2e_step()
+
+    def wall(fn):
+        fn()
+        timer.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            got = fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert got == S * F * NPTS * 10
+        if world > 1:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * S * F * NPTS * n_e2e / dt / 1e6
+
+    v_stitched = wall(stitched_step)
+    # the bytes the call returned for the last frame: header + this GPU's cameras against a device-side K1 of the same frame
+    last = hs[(F - 1) % NS]
+    hdr = int(last[:4].view(np.int32)[0])
+    chk = torch.zeros(S * NPTS * 10, dtype=torch.uint8, device="cuda")
+    zt = [torch.from_numpy(d_np[s, F - 1].view(np.int16)).cuda() for s in range(S)]
+    ct = [torch.from_numpy(c_np[s, F - 1]).cuda() for s in range(S)]
+    b = ctx.batch([(s, zt[s].data_ptr(), ct[s].data_ptr(), chk.data_ptr() + s * NPTS * 10) for s in range(S)])
+    b.run(torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    assert got == S * F * NPTS * 10
-    if world > 1:
-        t = torch.tensor([dt], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    return {"value": world * S * F * NPTS * n_e2e / dt / 1e6, "unit": "Mpoints/s",
-            "h2d_bytes_per_step": S * F * (NPTS * 2 + ch * cwb), "d2h_bytes_per_step": S * F * NPTS * 10,
-            "api": "pcs_b200_send_xyzrgb_begin/_end (host z16+RGB8 in, reference camera buffer out), "
-                   "%d cameras x %d frame(s) in flight, pinned host buffers" % (S, args.e2e_depth), "steps": n_e2e}
+    ok = hdr == S * NPTS * 10 and bool(np.array_equal(last[4:], chk.cpu().numpy()))
+    b.close()
+    v_camera = wall(camera_step)
+    v_probe = wall(probe_step)
+    h2d, d2h = S * F * (NPTS * 2 + ch * cwb), S * F * NPTS * 10 + 4 * F
+    return {"value": v_stitched, "unit": "Mpoints/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "api": "pcs_b200_stitch_frames_begin/_end (host z16+RGB8 of %d cameras in, the reference's stitched buffer "
+                   "[int32][records] out, one batched K1 launch + one D2H per stitched frame), %d frames in flight, pinned "
+                   "host buffers" % (S, NS),
+            "steps": n_e2e, "check": "ok" if ok else "MISMATCH",
+            "per_camera_api": {"value": v_camera, "api": "pcs_b200_send_xyzrgb_begin/_end (%d separate camera buffers, "
+                               "2 frames in flight)" % S},
+            "pcie_probe": {"value": v_probe, "what": "plain cudaMemcpyAsync of the same bytes per step (H2D per camera + one "
+                           "D2H per frame, one stream per frame in flight), no kernel", "d2h_GBps": v_probe * 1e6 * 10 / 1e9 / world,
+                           "h2d_GBps": v_probe * 1e6 * (2 + ch * cwb / NPTS) / 1e9 / world},
+            "frac_of_pcie": v_stitched / v_probe}
 
 
 if __name__ == "__main__":

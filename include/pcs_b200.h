@@ -213,6 +213,32 @@ PCS_API int pcs_b200_stitch_pcl(pcs_ctx *ctx, const int16_t *const *payload_host
                         int n_cams, int downsample, const float *transforms,
                         uint8_t *stitched_host, size_t stitched_cap);
 
+/* The whole camera -> stitcher path in one call, host buffers on both sides: depth + colour frames
+ * of n_cams cameras in, the reference's stitched buffer out.  Replaces, per frame,
+ * n_cams x (rs2::pointcloud::calculate + sendXYZRGBPointcloud, src/pcs-camera-optimized.cpp:288-292),
+ * the TCP fan-in of readCloud (src/pcs-multicamera-client.cpp:363-371) and the concat loop of
+ * sendStitchToUnity (:373-395): stitched_host receives [int32 payload bytes][records of streams[0]]
+ * [records of streams[1]]... with every `downsample`-th record of each camera kept (:388).
+ * Nothing returns to the host between the cameras' kernels and the concat: the frames go up, ONE
+ * batched launch of the fused kernel writes every camera's records into its slot of a device-resident
+ * stitched buffer, and one copy brings [int32][records] back.
+ *   slot          0 .. PCS_B200_STITCH_SLOTS-1: independent pipelines; a host thread keeps two frames
+ *                 in flight by alternating slots (begin(0) begin(1) end(0) begin(0) end(1) ...)
+ *   streams       n_cams stream ids (pcs_b200_set_stream), in stitched order; cutoff (-c) streams are
+ *                 not supported here (use pcs_b200_send_xyzrgb + pcs_b200_stitch_raw)
+ *   z16_host / color_host   n_cams frame pointers each; pinned memory (pcs_b200_host_alloc) lets the
+ *                 copies overlap the other slot's work
+ *   stitched_cap  bytes available at stitched_host
+ * begin() enqueues everything and returns; end() waits and returns the stitched payload bytes. */
+#define PCS_B200_STITCH_SLOTS 4
+PCS_API int pcs_b200_stitch_frames_begin(pcs_ctx *ctx, int slot, int n_cams, const int32_t *streams,
+                                 const uint16_t *const *z16_host, const uint8_t *const *color_host,
+                                 int downsample, uint8_t *stitched_host, size_t stitched_cap);
+PCS_API int pcs_b200_stitch_frames_end(pcs_ctx *ctx, int slot);
+PCS_API int pcs_b200_stitch_frames(pcs_ctx *ctx, int n_cams, const int32_t *streams,
+                           const uint16_t *const *z16_host, const uint8_t *const *color_host,
+                           int downsample, uint8_t *stitched_host, size_t stitched_cap);
+
 /* Voxel-grid merge of n records (own integer specification, oracle/SPEC.md s3; the
  * reference includes pcl/filters/voxel_grid.h but never calls it).  Returns the
  * number of voxels written to out_dev (capacity n records).  n * max(256, leaf_mm)

@@ -128,6 +128,10 @@ def _load():
         "pcs_b200_stitch_raw": (C.c_int, [vp, C.POINTER(vp), i32p, C.c_int, C.c_int, vp, C.c_size_t]),
         "pcs_b200_stitch_pcl_dev": (C.c_int, [vp, C.POINTER(vp), i32p, C.c_int, C.c_int, vp, vp, C.c_size_t, vp, vp]),
         "pcs_b200_stitch_pcl": (C.c_int, [vp, C.POINTER(vp), i32p, C.c_int, C.c_int, vp, vp, C.c_size_t]),
+        "pcs_b200_stitch_frames_begin": (C.c_int, [vp, C.c_int, C.c_int, i32p, C.POINTER(vp), C.POINTER(vp), C.c_int,
+                                                   vp, C.c_size_t]),
+        "pcs_b200_stitch_frames_end": (C.c_int, [vp, C.c_int]),
+        "pcs_b200_stitch_frames": (C.c_int, [vp, C.c_int, i32p, C.POINTER(vp), C.POINTER(vp), C.c_int, vp, C.c_size_t]),
         "pcs_b200_voxel_merge_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
         "pcs_b200_voxel_merge": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
         "pcs_b200_voxel_slab_plan_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, i32p, i32p, vp]),
@@ -335,6 +339,32 @@ class Context:
     def stitch_pcl(self, payloads, transforms, downsample=1):
         """unpack -> transform -> += -> repack: returns [int32 bytes][records] as uint8."""
         return self._stitch_host(payloads, downsample, transforms)
+
+    # ---- camera + stitch side in one call (host frames in, the reference's stitched buffer out)
+    STITCH_SLOTS = 4
+
+    def stitch_frames_begin(self, slot, streams, z16_frames, color_frames, stitched, downsample=1):
+        """Enqueue one stitched frame on pipeline `slot`: host z16 + colour frames of `streams` (stitched
+        order) in, `[int32 bytes][records]` into the host array `stitched` (uint8) once ``_end`` returns."""
+        n = len(streams)
+        ids = (C.c_int32 * n)(*streams)
+        zs = (C.c_void_p * n)(*[z.ctypes.data for z in z16_frames])
+        cs = (C.c_void_p * n)(*[c.ctypes.data for c in color_frames])
+        self._check(lib.pcs_b200_stitch_frames_begin(self.handle, slot, n, ids, zs, cs, downsample,
+                                                     _np_ptr(stitched), stitched.nbytes))
+
+    def stitch_frames_end(self, slot):
+        return self._check(lib.pcs_b200_stitch_frames_end(self.handle, slot))
+
+    def stitch_frames(self, streams, z16_frames, color_frames, downsample=1, stitched=None):
+        """sendXYZRGBPointcloud on every camera + sendStitchToUnity's concat: returns uint8 [int32][records]."""
+        z16_frames = [np.ascontiguousarray(z, np.uint16) for z in z16_frames]
+        color_frames = [np.ascontiguousarray(c, np.uint8) for c in color_frames]
+        if stitched is None:
+            stitched = np.zeros(4 + 10 * sum(z.size for z in z16_frames), np.uint8)
+        self.stitch_frames_begin(0, streams, z16_frames, color_frames, stitched, downsample)
+        size = self.stitch_frames_end(0)
+        return stitched[: size + 4]
 
     def voxel_merge(self, records, leaf_mm=10):
         rec = np.ascontiguousarray(records, np.int16).reshape(-1, 5)

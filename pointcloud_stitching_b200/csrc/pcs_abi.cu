@@ -18,6 +18,7 @@
 #include "pcs_k1_pipe.cuh"
 #include "pcs_voxel.cuh"
 #include "pcs_voxel_sweep.cuh"
+#include "pcs_voxel_msd.cuh"
 
 using namespace pcs;
 
@@ -59,6 +60,23 @@ struct StreamState {
     int pending_header = 0;
 };
 
+// One pipeline of pcs_b200_stitch_frames: device frames of every camera, the device-resident stitched
+// buffer all cameras write into, and the cached batch (job table + launch plan) of that camera set.
+struct StitchSlot {
+    std::mutex mu;
+    cudaStream_t cs = nullptr;
+    std::vector<int> streams;                 // what the cached plan was built for
+    std::vector<unsigned> gens;
+    int downsample = 0;
+    std::vector<uint16_t *> d_z;
+    std::vector<uint8_t *> d_c;
+    uint8_t *d_stitched = nullptr;            // [pad 12][int32][records of every camera, full rate]
+    uint8_t *d_decimated = nullptr;           // [pad 12][int32][records, every downsample-th]  (downsample > 1)
+    pcs_batch *batch = nullptr;
+    long long total_pts = 0, out_bytes = 0;
+    bool pending = false;
+};
+
 }  // namespace
 
 struct pcs_ctx {
@@ -76,6 +94,7 @@ struct pcs_ctx {
     uint8_t *d_stitch_in = nullptr, *d_stitch_out = nullptr;
     size_t cap_stitch_in = 0, cap_stitch_out = 0;
     VoxelScratch voxel;
+    StitchSlot stitch_slots[PCS_B200_STITCH_SLOTS];
 };
 
 struct pcs_batch {
@@ -328,7 +347,7 @@ int pcs_b200_create(const pcs_config *cfg, pcs_ctx **out) {
             return fail(nullptr, PCS_ERR_CUDA, "cudaStreamCreate failed");
         }
     int rc = pipe_configure(ctx->device);
-    if (rc == PCS_OK && (sweep_configure<8, 256, 16>() != 0 || sweep_configure<10, 256, 16>() != 0))
+    if (rc == PCS_OK && (sweep_configure<8, 256, 16>() != 0 || sweep_configure<10, 256, 16>() != 0 || vm_configure() != 0))
         rc = PCS_ERR_CUDA;
     if (rc != PCS_OK) {
         pcs_b200_destroy(ctx);
@@ -356,6 +375,13 @@ void pcs_b200_destroy(pcs_ctx *ctx) {
     cudaFree(ctx->d_stitch_in);
     cudaFree(ctx->d_stitch_out);
     voxel_free(ctx->voxel);
+    for (StitchSlot &sl : ctx->stitch_slots) {
+        if (sl.cs) { cudaStreamSynchronize(sl.cs); cudaStreamDestroy(sl.cs); }
+        for (auto *p : sl.d_z) cudaFree(p);
+        for (auto *p : sl.d_c) cudaFree(p);
+        cudaFree(sl.d_stitched); cudaFree(sl.d_decimated);
+        if (sl.batch) pcs_b200_batch_destroy(ctx, sl.batch);
+    }
     delete ctx;
 }
 
@@ -890,6 +916,133 @@ int pcs_b200_stitch_pcl(pcs_ctx *ctx, const int16_t *const *payload_host, const 
     return stitch_host(ctx, payload_host, n_shorts, n_cams, downsample, transforms, true, stitched_host, stitched_cap);
 }
 
+// ---- camera + stitch side in one call, host buffers ------------------------------------------
+// (Re)builds a slot's device buffers and launch plan for a camera set.  Called under the slot lock.
+static int stitch_slot_prepare(pcs_ctx *ctx, StitchSlot &sl, int n_cams, const int32_t *streams, int downsample) {
+    bool same = sl.batch && (int)sl.streams.size() == n_cams && sl.downsample == downsample;
+    for (int i = 0; same && i < n_cams; ++i)
+        same = sl.streams[i] == streams[i] && sl.gens[i] == ctx->streams[streams[i]].geom_gen;
+    if (same) return PCS_OK;
+    if (!sl.cs) CU(ctx, cudaStreamCreateWithFlags(&sl.cs, cudaStreamNonBlocking));
+    CU(ctx, cudaStreamSynchronize(sl.cs));
+    for (auto *p : sl.d_z) cudaFree(p);
+    for (auto *p : sl.d_c) cudaFree(p);
+    cudaFree(sl.d_stitched); cudaFree(sl.d_decimated);
+    if (sl.batch) pcs_b200_batch_destroy(ctx, sl.batch);
+    sl.d_z.clear(); sl.d_c.clear(); sl.d_stitched = sl.d_decimated = nullptr; sl.batch = nullptr;
+    sl.streams.clear(); sl.gens.clear();
+    long long total = 0, out = 0;
+    for (int i = 0; i < n_cams; ++i) {
+        const StreamParams &p = ctx->streams[streams[i]].params;
+        total += p.N;
+        out += (p.N + downsample - 1) / downsample;
+    }
+    if (total * 10 > 0x7fffffffll) return fail(ctx, PCS_ERR_CAPACITY, "stitched payload exceeds int32");
+    std::vector<pcs_frame_job> jobs(n_cams);
+    auto oom = [&]() { cudaGetLastError(); return fail(ctx, PCS_ERR_NOMEM, "stitch_frames: device allocation failed"); };
+    if (cudaMalloc(&sl.d_stitched, (size_t)total * 10 + 32) != cudaSuccess) return oom();
+    if (downsample > 1 && cudaMalloc(&sl.d_decimated, (size_t)out * 10 + 32) != cudaSuccess) return oom();
+    long long off = 0;
+    for (int i = 0; i < n_cams; ++i) {
+        const StreamParams &p = ctx->streams[streams[i]].params;
+        uint16_t *z = nullptr;
+        uint8_t *c = nullptr;
+        if (cudaMalloc(&z, (size_t)p.N * 2 + 64) != cudaSuccess) return oom();
+        sl.d_z.push_back(z);
+        if (cudaMalloc(&c, (size_t)p.CH * p.stride + 64) != cudaSuccess) return oom();
+        sl.d_c.push_back(c);
+        jobs[i] = pcs_frame_job{};
+        jobs[i].stream = streams[i];
+        jobs[i].z16_dev = z;
+        jobs[i].color_dev = c;
+        jobs[i].payload_dev = reinterpret_cast<int16_t *>(sl.d_stitched + 16 + off * 10);
+        off += p.N;
+    }
+    int rc = pcs_b200_batch_create(ctx, jobs.data(), n_cams, &sl.batch);
+    if (rc) return rc;
+    // the int32 size header never changes for a camera set (no cutoff here): written once
+    const int32_t full = (int32_t)(total * 10), dec = (int32_t)(out * 10);
+    CU(ctx, cudaMemcpy(sl.d_stitched + 12, &full, 4, cudaMemcpyHostToDevice));
+    if (sl.d_decimated) CU(ctx, cudaMemcpy(sl.d_decimated + 12, &dec, 4, cudaMemcpyHostToDevice));
+    sl.total_pts = total;
+    sl.out_bytes = out * 10;
+    sl.downsample = downsample;
+    sl.streams.assign(streams, streams + n_cams);
+    for (int i = 0; i < n_cams; ++i) sl.gens.push_back(ctx->streams[streams[i]].geom_gen);
+    return PCS_OK;
+}
+
+int pcs_b200_stitch_frames_begin(pcs_ctx *ctx, int slot, int n_cams, const int32_t *streams,
+                                 const uint16_t *const *z16_host, const uint8_t *const *color_host,
+                                 int downsample, uint8_t *stitched_host, size_t stitched_cap) {
+    if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
+    if (slot < 0 || slot >= PCS_B200_STITCH_SLOTS) return fail(ctx, PCS_ERR_INVALID, "slot out of range");
+    if (n_cams < 1 || n_cams > MAX_CAMS || !streams || !z16_host || !color_host || !stitched_host || downsample < 1)
+        return fail(ctx, PCS_ERR_INVALID, "bad stitch_frames arguments (1 <= n_cams <= %d)", MAX_CAMS);
+    for (int i = 0; i < n_cams; ++i) {
+        int rc = check_stream(ctx, streams[i], true);
+        if (rc) return rc;
+        if (ctx->streams[streams[i]].params.cutoff)
+            return fail(ctx, PCS_ERR_UNSUPPORTED, "stream %d has cutoff set: use pcs_b200_send_xyzrgb + pcs_b200_stitch_raw", streams[i]);
+        if (!z16_host[i] || !color_host[i]) return fail(ctx, PCS_ERR_INVALID, "camera %d: null frame", i);
+    }
+    StitchSlot &sl = ctx->stitch_slots[slot];
+    std::lock_guard<std::mutex> lk(sl.mu);
+    if (sl.pending) return fail(ctx, PCS_ERR_INVALID, "slot %d already has a frame in flight", slot);
+    DeviceGuard dg_(ctx->device);
+    int rc = stitch_slot_prepare(ctx, sl, n_cams, streams, downsample);
+    if (rc) return rc;
+    if ((size_t)sl.out_bytes + 4 > stitched_cap)
+        return fail(ctx, PCS_ERR_CAPACITY, "stitched buffer too small: need %lld bytes", sl.out_bytes + 4);
+    for (int i = 0; i < n_cams; ++i) {
+        const StreamParams &p = ctx->streams[streams[i]].params;
+        CU(ctx, cudaMemcpyAsync(sl.d_z[i], z16_host[i], (size_t)p.N * 2, cudaMemcpyHostToDevice, sl.cs));
+        CU(ctx, cudaMemcpyAsync(sl.d_c[i], color_host[i], (size_t)p.CH * p.stride, cudaMemcpyHostToDevice, sl.cs));
+    }
+    if ((rc = pcs_b200_batch_run(ctx, sl.batch, sl.cs))) return rc;
+    const uint8_t *src = sl.d_stitched + 12;
+    if (downsample > 1) {
+        // every downsample-th record of each camera (src/pcs-multicamera-client.cpp:388), device to device
+        std::vector<const int16_t *> pay(n_cams);
+        std::vector<int32_t> ns(n_cams);
+        long long off = 0;
+        for (int i = 0; i < n_cams; ++i) {
+            const StreamParams &p = ctx->streams[streams[i]].params;
+            pay[i] = reinterpret_cast<const int16_t *>(sl.d_stitched + 16 + off * 10);
+            ns[i] = p.N * 5;
+            off += p.N;
+        }
+        rc = stitch_common(ctx, pay.data(), ns.data(), n_cams, downsample, nullptr, false, sl.d_decimated + 12,
+                           (size_t)sl.out_bytes + 4, nullptr, sl.cs);
+        if (rc < 0) return rc;
+        src = sl.d_decimated + 12;
+    }
+    CU(ctx, cudaMemcpyAsync(stitched_host, src, (size_t)sl.out_bytes + 4, cudaMemcpyDeviceToHost, sl.cs));
+    sl.pending = true;
+    return PCS_OK;
+}
+
+int pcs_b200_stitch_frames_end(pcs_ctx *ctx, int slot) {
+    if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
+    if (slot < 0 || slot >= PCS_B200_STITCH_SLOTS) return fail(ctx, PCS_ERR_INVALID, "slot out of range");
+    StitchSlot &sl = ctx->stitch_slots[slot];
+    std::lock_guard<std::mutex> lk(sl.mu);
+    if (!sl.pending) return fail(ctx, PCS_ERR_INVALID, "slot %d has no frame in flight", slot);
+    sl.pending = false;
+    DeviceGuard dg_(ctx->device);
+    CU(ctx, cudaStreamSynchronize(sl.cs));
+    return (int)sl.out_bytes;
+}
+
+int pcs_b200_stitch_frames(pcs_ctx *ctx, int n_cams, const int32_t *streams, const uint16_t *const *z16_host,
+                           const uint8_t *const *color_host, int downsample, uint8_t *stitched_host,
+                           size_t stitched_cap) {
+    int rc = pcs_b200_stitch_frames_begin(ctx, 0, n_cams, streams, z16_host, color_host, downsample, stitched_host,
+                                          stitched_cap);
+    if (rc) return rc;
+    return pcs_b200_stitch_frames_end(ctx, 0);
+}
+
 // ---- voxel merge -----------------------------------------------------------------
 static int voxel_args_ok(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, const void *out) {
     if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
@@ -907,6 +1060,34 @@ static int voxel_fail(pcs_ctx *ctx, int rc) {
                 "voxel merge failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
 }
 
+// voxel_variant: 0 = auto (MSD partition + bitmap ranking when the cloud fits its limits, else the one-sweep
+// sort when the (key, index) word fits 64 bits, else the pair sort), 1 = pair sort, 2 / 3 = one-sweep sort with
+// 8- / 10-bit digits, 4 = MSD only
+static int voxel_run(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, int16_t *out_dev, cudaStream_t cs,
+                     bool slab, int kz_lo, int kz_hi) {
+    const int vv = ctx->voxel_variant;
+    int rc = -4;
+    if (vv == 0 || vv == 4) {
+        int32_t *nv_dev = nullptr;
+        rc = voxel_merge_msd(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, slab, kz_lo, kz_hi, &nv_dev);
+        if (rc == 0) {
+            if (cudaMemcpyAsync(ctx->voxel.h_count, nv_dev, 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
+                cudaStreamSynchronize(cs) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+                return -2;
+            const int nv = ctx->voxel.h_count[0];
+            return (nv < 0 || nv > n) ? -2 : nv;
+        }
+        if (vv == 4 || rc != -4) return rc;
+    }
+    if (vv == 3)
+        rc = voxel_merge_sweep<10, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, slab, kz_lo, kz_hi);
+    else if (vv == 0 || vv == 2 || slab)
+        rc = voxel_merge_sweep<8, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, slab, kz_lo, kz_hi);
+    if (!slab && (vv == 1 || (vv == 0 && rc == -4)))
+        rc = voxel_merge(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs);
+    return rc;
+}
+
 int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
                              int16_t *out_dev, void *cuda_stream) {
     int rc = voxel_args_ok(ctx, records_dev, n, leaf_mm, out_dev);
@@ -914,15 +1095,7 @@ int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, in
     if (n == 0) return 0;
     DeviceGuard dg_(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->scratch_mu);
-    // voxel_variant: 0 = one-sweep sort when the (key, index) word fits 64 bits, else the pair sort
-    rc = -4;
-    const int vv = ctx->voxel_variant;
-    if (vv == 3)
-        rc = voxel_merge_sweep<10, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream, ctx->sm_count);
-    else if (vv == 0 || vv == 2)
-        rc = voxel_merge_sweep<8, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream, ctx->sm_count);
-    if (vv == 1 || (vv == 0 && rc == -4))
-        rc = voxel_merge(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream);
+    rc = voxel_run(ctx, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream, false, 0, 0);
     return rc < 0 ? voxel_fail(ctx, rc) : rc;
 }
 
@@ -945,12 +1118,7 @@ int pcs_b200_voxel_merge_slab_dev(pcs_ctx *ctx, const int16_t *records_dev, int 
     if (n == 0 || kz_lo >= kz_hi) return 0;
     DeviceGuard dg_(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->scratch_mu);
-    if (ctx->voxel_variant == 3)
-        rc = voxel_merge_sweep<10, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream,
-                                            ctx->sm_count, true, kz_lo, kz_hi);
-    else
-        rc = voxel_merge_sweep<8, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream,
-                                           ctx->sm_count, true, kz_lo, kz_hi);
+    rc = voxel_run(ctx, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream, true, kz_lo, kz_hi);
     return rc < 0 ? voxel_fail(ctx, rc) : rc;
 }
 

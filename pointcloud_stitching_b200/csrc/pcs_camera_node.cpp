@@ -13,6 +13,7 @@
 #include <sys/socket.h>
 #include <unistd.h>
 
+#include <csignal>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -71,6 +72,7 @@ int main(int argc, char **argv) {
         else if (a == "--push") push = true;
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
+    signal(SIGPIPE, SIG_IGN);
     const size_t n = (size_t)w * h;
     std::vector<uint8_t> depth, color;
     if (!read_file(depth_path, depth, n * 2 * frames) || !read_file(color_path, color, n * 3 * frames)) {

@@ -26,12 +26,15 @@ struct VoxelScratch {
     uint8_t *buf = nullptr;
     size_t cap = 0;
     int32_t *h_count = nullptr;   // pinned
+    uint8_t *h_tab = nullptr;     // pinned staging for the MSD merge's plan tables
+    size_t h_tab_cap = 0;
 };
 
 inline void voxel_free(VoxelScratch &s) {
     cudaFree(s.buf);
     if (s.h_count) cudaFreeHost(s.h_count);
-    s.buf = nullptr; s.cap = 0; s.h_count = nullptr;
+    if (s.h_tab) cudaFreeHost(s.h_tab);
+    s.buf = nullptr; s.cap = 0; s.h_count = nullptr; s.h_tab = nullptr; s.h_tab_cap = 0;
 }
 
 struct VoxelGeom {

@@ -172,9 +172,10 @@ def test_stitch_errors(ctx):
     assert e.value.status == pcs.PCS_ERR_CAPACITY
 
 
-@pytest.fixture(scope="module", params=[0, 1, 2, 3], ids=["auto", "pair_sort", "sweep8", "sweep10"])
+@pytest.fixture(scope="module", params=[0, 1, 2, 3, 4], ids=["auto", "pair_sort", "sweep8", "sweep10", "msd"])
 def vctx(request):
-    """One context per voxel_variant: auto, the (key, index) pair sort, the one-sweep sort (8 / 10 bit)."""
+    """One context per voxel_variant: auto (MSD partition + bitmap ranking, falling back to the sorts), the
+    (key, index) pair sort, the one-sweep sort (8 / 10 bit), MSD only."""
     c = pcs.Context(device=0, max_streams=2, voxel_variant=request.param)
     c.variant = request.param
     yield c
@@ -185,10 +186,19 @@ def test_voxel_merge_vs_oracle(vctx, R):
     rng = np.random.default_rng(11)
     cases = [(50000, 2000, 10), (200000, 400, 10), (5000, 30000, 25), (4, 10, 10), (1, 5, 1), (4096, 300, 10),
              (4097, 300, 10), (8191, 20, 10), (255, 3, 10), (257, 40000, 10), (70001, 60, 3)]
+    exact = 0
     for n, span, leaf in cases:
         rec = random_records(rng, n)
         rec[:, :3] = rng.integers(-span, span, (n, 3))
-        assert np.array_equal(vctx.voxel_merge(rec, leaf), R.voxel_merge(rec, leaf)), (n, span, leaf)
+        try:
+            got = vctx.voxel_merge(rec, leaf)
+        except pcs.PcsError as e:
+            # MSD only: a z plane of the occupied box may hold at most 2^24 voxels, in at most 1024 slabs
+            assert vctx.variant == 4 and e.status == pcs.PCS_ERR_UNSUPPORTED and span >= 30000, (n, span, leaf)
+            continue
+        assert np.array_equal(got, R.voxel_merge(rec, leaf)), (n, span, leaf)
+        exact += 1
+    assert exact >= len(cases) - 2
     assert len(vctx.voxel_merge(np.zeros((0, 5), np.int16), 10)) == 0
 
 
@@ -248,7 +258,7 @@ def test_voxel_merge_wide_keys_fall_back(vctx, R):
     rng = np.random.default_rng(14)
     n = 150000
     rec = random_records(rng, n)
-    if vctx.variant in (2, 3):
+    if vctx.variant in (2, 3, 4):
         with pytest.raises(pcs.PcsError) as e:
             vctx.voxel_merge(rec, 1)
         assert e.value.status == pcs.PCS_ERR_UNSUPPORTED
@@ -303,3 +313,77 @@ def test_baseline_configs_k1_concat_voxel(ctx, R, n_cams, w, h):
     assert np.array_equal(out[: nv * 5].cpu().numpy().reshape(-1, 5), want_vox)
     b.close()
     c2.close()
+
+
+# ---- the whole path in one call: host frames in, the reference's stitched buffer out ------------------
+@pytest.mark.parametrize("downsample", [1, 2, 3])
+def test_stitch_frames_host_api_vs_oracle(R, downsample):
+    """pcs_b200_stitch_frames == n x (calculate + sendXYZRGBPointcloud) + readCloud + sendStitchToUnity's concat
+    (src/pcs-camera-optimized.cpp:288-292, src/pcs-multicamera-client.cpp:363-395), mixed geometries."""
+    geoms = [(1280, 720, synth.D2C_BASELINE), (848, 480, (0.0, 0.0, 0.0)), (1280, 720, (0.0, 0.0, 0.0)),
+             (640, 480, synth.D2C_BASELINE)]
+    c = pcs.Context(device=0, max_streams=len(geoms))
+    zs, cols, want = [], [], []
+    for cam, (w, h, tr) in enumerate(geoms):
+        c.set_stream(cam, pcs.stream_desc(w, h, tf=synth.TF_STITCH[cam], translation=tr))
+        z, col = synth.depth_frame(w, h, cam, 3), synth.color_frame(w, h, cam, 3)
+        zs.append(z)
+        cols.append(col)
+        want.append(R.frame(oracle.make_calib(w, h, translation=tr), z, col, 3, w * 3, synth.TF_STITCH[cam]).reshape(-1))
+    order = [2, 0, 3, 1]     # stitched order is the order of `streams`, not of the stream ids
+    got = c.stitch_frames(order, [zs[i] for i in order], [cols[i] for i in order], downsample)
+    assert np.array_equal(got, R.concat([want[i] for i in order], downsample))
+    # two frames in flight on two slots, and a slot reused for another camera set
+    bufs = [np.zeros(4 + 10 * sum(z.size for z in zs), np.uint8) for _ in range(2)]
+    c.stitch_frames_begin(0, [0, 1], zs[:2], cols[:2], bufs[0], downsample)
+    c.stitch_frames_begin(1, [3], zs[3:], cols[3:], bufs[1], downsample)
+    n0, n1 = c.stitch_frames_end(0), c.stitch_frames_end(1)
+    assert np.array_equal(bufs[0][: n0 + 4], R.concat(want[:2], downsample))
+    assert np.array_equal(bufs[1][: n1 + 4], R.concat(want[3:], downsample))
+    with pytest.raises(pcs.PcsError):
+        c.stitch_frames_end(0)                      # nothing in flight
+    with pytest.raises(pcs.PcsError):
+        c.stitch_frames([0], zs[:1], cols[:1], 1, stitched=np.zeros(100, np.uint8))   # too small
+    c.close()
+
+
+def test_voxel_merge_msd_shapes(R):
+    """The MSD partition's corner cases: dense planes (thousands of points per z plane and per key row), a
+    cloud that is one z plane, one voxel row, leaf sizes up to 32 mm, a sub-bucket that needs several
+    accumulator rounds, and the z-slab filter with empty slabs inside the range."""
+    c = pcs.Context(device=0, max_streams=1, voxel_variant=4)
+    rng = np.random.default_rng(21)
+
+    def check(rec, leaf):
+        assert np.array_equal(c.voxel_merge(rec, leaf), R.voxel_merge(rec, leaf)), (len(rec), leaf)
+
+    n = 400000
+    # a wall in one z plane (x, y spread; ~ 1 point per voxel) + a floor (one y row band) + a dense blob
+    rec = random_records(rng, n)
+    rec[:, 0] = rng.integers(-2000, 2000, n)
+    rec[:, 1] = rng.integers(-1200, 1200, n)
+    rec[:, 2] = 1503
+    rec[: n // 4, 1] = -1195
+    rec[: n // 4, 2] = rng.integers(500, 4000, n // 4)
+    rec[n // 4: n // 4 + 50000, :3] = rng.integers(100, 160, (50000, 3))      # 6^3 voxels, ~230 points each
+    check(rec, 10)
+    # one voxel row, every voxel hit ~100 times
+    rec = random_records(rng, 100000)
+    rec[:, 0] = rng.integers(-5000, 5000, 100000)
+    rec[:, 1:3] = (77, -3)
+    check(rec, 10)
+    # leaf sizes: offsets of 1 .. 5 bits
+    for leaf in (1, 2, 5, 16, 17, 32):
+        rec = random_records(rng, 60000)
+        rec[:, :3] = rng.integers(-40 * leaf, 40 * leaf, (60000, 3))
+        check(rec, leaf)
+    with pytest.raises(pcs.PcsError):
+        c.voxel_merge(rec, 33)
+    # many voxels in one sub-bucket range (several accumulator rounds) next to empty space
+    rec = random_records(rng, 30000)
+    rec[:, 0] = rng.integers(0, 1270, 30000)
+    rec[:, 1] = rng.integers(0, 100, 30000)
+    rec[:, 2] = 0
+    rec[-1, :3] = (30000, 30000, 3000)        # stretches the box
+    check(rec, 10)
+    c.close()

@@ -140,3 +140,144 @@ def test_reference_stitcher_with_b200_camera_node(restatement, tmp_path):
     for f in range(FRAMES):
         assert _same_cloud(got[f], want[f]), "frame %d\n%s" % (f, out)
     assert "frames sent" in out
+
+
+# ---- the rest of SURVEY s8(f) rank 1: push-mode camera, and the stitcher tier serving a viewer on its own port --------
+STITCH_BIN = os.path.join(ROOT, "pointcloud_stitching_b200", "pcs_stitch_node")
+
+
+def _free_ports(k):
+    socks = [socket.socket() for _ in range(k)]
+    for s in socks:
+        s.bind(("127.0.0.1", 0))
+    ports = [s.getsockname()[1] for s in socks]
+    for s in socks:
+        s.close()
+    return ports
+
+
+def _consecutive_free_ports(k):
+    for base in range(18000, 30000, 16):
+        if all(_port_free(base + i) for i in range(k)):
+            return base
+    raise RuntimeError("no free port range")
+
+
+def _connect(port, timeout=90):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        try:
+            return socket.create_connection(("127.0.0.1", port), timeout=60)
+        except OSError:
+            time.sleep(0.1)
+    raise RuntimeError("nobody listens on :%d" % port)
+
+
+def _read_exact(sock, n):
+    buf = bytearray()
+    while len(buf) < n:
+        chunk = sock.recv(min(1 << 20, n - len(buf)))
+        if not chunk:
+            raise EOFError("peer closed after %d of %d bytes" % (len(buf), n))
+        buf += chunk
+    return bytes(buf)
+
+
+def _read_frame(sock):
+    n = int(np.frombuffer(_read_exact(sock, 4), np.int32)[0])
+    return np.frombuffer(_read_exact(sock, n), np.int16)
+
+
+def _camera_files(tmp_path, cam, w, h, frames):
+    d, c = tmp_path / ("depth%d.raw" % cam), tmp_path / ("color%d.raw" % cam)
+    np.stack([synth.depth_frame(w, h, cam, f) for f in range(frames)]).tofile(d)
+    np.stack([synth.color_frame(w, h, cam, f) for f in range(frames)]).tofile(c)
+    return str(d), str(c)
+
+
+def _finish(proc, what):
+    try:
+        out, _ = proc.communicate(timeout=30)
+    except subprocess.TimeoutExpired:
+        proc.kill()
+        out, _ = proc.communicate()
+    return out
+
+
+@pytest.mark.gpu
+def test_push_mode_camera_node(restatement, tmp_path):
+    """`pcs-camera-optimized -f X -s` (src/pcs-camera-optimized.cpp:264-302): every frame is sent without waiting
+    for a pull.  The reader below never writes a byte -- what pcs-multicamera-client's readCloud does before
+    its first pull (src/pcs-multicamera-client.cpp:363-371)."""
+    import oracle
+    w, h, frames, loops = 848, 480, 2, 5
+    port, = _free_ports(1)
+    d, c = _camera_files(tmp_path, 3, w, h, frames)
+    node = subprocess.Popen([NODE_BIN, "--depth", d, "--color", c, "--w", str(w), "--h", str(h), "--frames", str(frames),
+                             "--tx", "0.015", "--tf", "0", "--port", str(port), "--push", "--loops", str(loops)],
+                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    cal = oracle.make_calib(w, h, translation=synth.D2C_BASELINE)
+    want = [restatement.frame(cal, synth.depth_frame(w, h, 3, f), synth.color_frame(w, h, 3, f), 3, w * 3, synth.TF_CAMERA)
+            for f in range(frames)]
+    try:
+        s = _connect(port)
+        for f in range(loops):
+            assert np.array_equal(_read_frame(s), want[f % frames].reshape(-1)), "frame %d" % f
+        assert s.recv(1) == b""            # the node closes after --loops frames
+        s.close()
+    finally:
+        out = _finish(node, "camera")
+    assert "%d frames sent" % loops in out, out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["push_raw_d1", "pull_raw_d3", "pull_pcl_d2"])
+def test_stitch_node_serves_the_viewer(restatement, tmp_path, mode):
+    """The stitcher tier end to end: two GPU camera nodes -> pcs_stitch_node (readCloud threads, GPU stitch) -> a viewer
+    that pulls [int32][stitched] with 'Z' on the server port (src/pcs-multicamera-client.cpp:398-403;
+    src/pcs-multicamera-optimized.cpp:299-313).  Both flow-control modes of SURVEY F11."""
+    import oracle
+    push, pcl, d = mode.startswith("push"), "pcl" in mode, int(mode[-1])
+    geoms = [(848, 480), (640, 480)]
+    frames, served = 2, 3
+    base = _consecutive_free_ports(3)
+    cam_port, viewer_port = base, base + 2
+    nodes, want_pay = [], []
+    for cam, (w, h) in enumerate(geoms):
+        dp, cp = _camera_files(tmp_path, cam, w, h, frames)
+        args = [NODE_BIN, "--depth", dp, "--color", cp, "--w", str(w), "--h", str(h), "--frames", str(frames), "--tx", "0.015",
+                "--tf", "0", "--port", str(cam_port + cam)]
+        if push:
+            args += ["--push", "--loops", str(served)]
+        nodes.append(subprocess.Popen(args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        cal = oracle.make_calib(w, h, translation=synth.D2C_BASELINE)
+        want_pay.append([restatement.frame(cal, synth.depth_frame(w, h, cam, f), synth.color_frame(w, h, cam, f), 3, w * 3,
+                                           synth.TF_CAMERA) for f in range(frames)])
+    sargs = [STITCH_BIN, "--cameras", "2", "--camera-port", str(cam_port), "--viewer-port", str(viewer_port), "--downsample",
+             str(d), "--frames", str(served)]
+    if not push:
+        sargs.append("--prime-pull")
+    tfs = [synth.TF_STITCH[2], synth.TF_STITCH[5]]
+    if pcl:
+        import json
+        tf_file = tmp_path / "rig.json"
+        tf_file.write_text(json.dumps({"left": np.asarray(tfs[0], np.float64).reshape(4, 4).tolist(),
+                                       "right": np.asarray(tfs[1], np.float64).reshape(4, 4).tolist()}))
+        sargs += ["--pcl", "--tf-file", str(tf_file), "--names", "left,right"]
+    stitcher = subprocess.Popen(sargs, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        v = _connect(viewer_port)
+        for f in range(served):
+            v.sendall(b"Z")
+            got = _read_frame(v)
+            pays = [want_pay[cam][f % frames] for cam in range(2)]
+            if pcl:
+                want = restatement.pcl_stitch(pays, tfs, d)
+            else:
+                want = restatement.concat([p.reshape(-1) for p in pays], d)
+            assert np.array_equal(got, np.frombuffer(want[4:].tobytes(), np.int16)), "stitched frame %d (%s)" % (f, mode)
+        v.close()
+    finally:
+        sout = _finish(stitcher, "stitcher")
+        outs = [_finish(n, "camera") for n in nodes]
+    assert "%d stitched frames served" % served in sout, sout + "".join(outs)
