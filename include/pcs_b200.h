@@ -87,7 +87,8 @@ typedef struct pcs_config {
     int32_t device;            /* CUDA device ordinal */
     int32_t max_streams;       /* camera streams this context serves (>= 1) */
     int32_t kernel_variant;    /* 0 = auto, 1 = direct (LDG/STG), 2 = bulk-async pipelined (TMA) */
-    int32_t voxel_variant;     /* 0 = auto, 1 = (key, index) pair sort, 2 / 3 = one-sweep sort, 8- / 10-bit digits */
+    int32_t voxel_variant;     /* 0 = auto (2, else 4, else 1), 1 = (key, index) pair sort, 2 / 3 = one-sweep sort with
+                                  8- / 10-bit digits, 4 = slab partition + bitmap ranking (no sort, any n) */
 } pcs_config;
 
 /* One frame of work for the batched device-resident path. */
@@ -178,6 +179,25 @@ PCS_API int pcs_b200_batch_launches(const pcs_batch *batch);
  * GPU each map peer memory with CUDA IPC / symmetric memory instead. */
 PCS_API int pcs_b200_enable_peer(pcs_ctx *ctx, int peer_device);
 
+/* Hosts that run ONE PROCESS PER GPU (the reference's deployment: one process per camera, fan-in over TCP,
+ * src/pcs-multicamera-client.cpp:363-371): a process exports the device memory that holds its cameras'
+ * frames (or its stitched mirror), sends the 80-byte handle to its peers over whatever channel it has (a
+ * socket, MPI, a file) and every peer maps it with pcs_b200_ipc_open.  The mapped pointer is an ordinary
+ * device pointer on the opener's GPU: it can be a job's z16_dev / color_dev (pull exchange, the peer's frames
+ * are read over NVLink by the fused kernel itself) or a peer base of pcs_b200_batch_create_fanout.  dev_ptr may
+ * point anywhere inside a cudaMalloc allocation (the handle records the offset).  The exporter must keep the
+ * allocation alive until every opener has called pcs_b200_ipc_close; synchronising the processes around a
+ * frame (nobody overwrites a frame that a peer is still reading) stays with the host, as it does for the
+ * sockets of the reference. */
+typedef struct pcs_ipc_handle {
+    uint8_t reserved[64];      /* cudaIpcMemHandle_t of the allocation */
+    uint64_t offset;           /* dev_ptr - allocation base */
+    uint64_t device;           /* exporter's CUDA device ordinal (informative) */
+} pcs_ipc_handle;
+PCS_API int pcs_b200_ipc_export(pcs_ctx *ctx, const void *dev_ptr, pcs_ipc_handle *out);
+PCS_API int pcs_b200_ipc_open(pcs_ctx *ctx, const pcs_ipc_handle *handle, void **dev_ptr_out);
+PCS_API int pcs_b200_ipc_close(pcs_ctx *ctx, void *dev_ptr);
+
 /* Device-pointer form of pcs_b200_pack_from_vertices; asynchronous on cuda_stream.  Without cutoff
  * the return value is the record count (n).  With cutoff (-c) the count is only known on the
  * device: it is written to *count_dev (required then, PCS_ERR_INVALID if NULL) and the return value
@@ -241,9 +261,11 @@ PCS_API int pcs_b200_stitch_frames(pcs_ctx *ctx, int n_cams, const int32_t *stre
 
 /* Voxel-grid merge of n records (own integer specification, oracle/SPEC.md s3; the
  * reference includes pcl/filters/voxel_grid.h but never calls it).  Returns the
- * number of voxels written to out_dev (capacity n records).  n * max(256, leaf_mm)
- * must stay below 2^32 (uint32 sums: n < 16.8 M points at the 10 mm leaf).  The call
- * synchronises cuda_stream once (the voxel count has to reach the host). */
+ * number of voxels written to out_dev (capacity n records).  The sort-based variants need
+ * n * max(256, leaf_mm) < 2^32 (uint32 sums: 16.7 M points at the 10 mm leaf); larger clouds, up to what
+ * the reference's int32 size header can describe (n * 10 < 2^31), take the slab-partition variant when
+ * leaf <= 32 mm and a z plane of the occupied box holds <= 2^24 voxels (40 m x 40 m at the 10 mm leaf).
+ * The call synchronises cuda_stream (the voxel count has to reach the host). */
 PCS_API int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
                              int16_t *out_dev, void *cuda_stream);
 PCS_API int pcs_b200_voxel_merge(pcs_ctx *ctx, const int16_t *records_host, int n, int leaf_mm,

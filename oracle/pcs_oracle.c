@@ -247,18 +247,19 @@ int pcs_oracle_voxel_merge(const int16_t *records, int n, int leaf_mm, int16_t *
     int nv = 0;
     for (int i = 0; i < n;) {
         int j = i;
-        uint32_t sx = 0, sy = 0, sz = 0, sr = 0, sg = 0, sb = 0, cnt = 0;
+        /* 64-bit sums: exact integer means for any n (SPEC.md s3 said uint32 when n * 255 < 2^32 was an ABI limit) */
+        uint64_t sx = 0, sy = 0, sz = 0, sr = 0, sg = 0, sb = 0, cnt = 0;
         const int kx = (int)(it[i].key & 0x1FFFF) - 32768;
         const int ky = (int)((it[i].key >> 17) & 0x1FFFF) - 32768;
         const int kz = (int)((it[i].key >> 34) & 0x1FFFF) - 32768;
         for (; j < n && it[j].key == it[i].key; ++j) {
             const int16_t *r = records + 5 * (size_t)it[j].idx;
-            sx += (uint32_t)(r[0] - leaf_mm * kx);
-            sy += (uint32_t)(r[1] - leaf_mm * ky);
-            sz += (uint32_t)(r[2] - leaf_mm * kz);
-            sr += (uint32_t)((uint16_t)r[3] & 0xFF);
-            sg += (uint32_t)((uint16_t)r[3] >> 8);
-            sb += (uint32_t)((uint16_t)r[4] & 0xFF);
+            sx += (uint64_t)(r[0] - leaf_mm * kx);
+            sy += (uint64_t)(r[1] - leaf_mm * ky);
+            sz += (uint64_t)(r[2] - leaf_mm * kz);
+            sr += (uint64_t)((uint16_t)r[3] & 0xFF);
+            sg += (uint64_t)((uint16_t)r[3] >> 8);
+            sb += (uint64_t)((uint16_t)r[4] & 0xFF);
             ++cnt;
         }
         int16_t *o = out + 5 * (size_t)nv;

@@ -56,6 +56,10 @@ class Config(C.Structure):
                 ("voxel_variant", C.c_int32)]
 
 
+class IpcHandle(C.Structure):
+    _fields_ = [("reserved", C.c_uint8 * 64), ("offset", C.c_uint64), ("device", C.c_uint64)]
+
+
 class FrameJob(C.Structure):
     _fields_ = [("stream", C.c_int32), ("reserved", C.c_int32), ("z16_dev", C.c_void_p),
                 ("color_dev", C.c_void_p), ("payload_dev", C.c_void_p), ("xyzrgb_dev", C.c_void_p),
@@ -121,6 +125,9 @@ def _load():
         "pcs_b200_batch_create_fanout": (C.c_int, [vp, C.POINTER(FrameJob), C.c_int, vp, C.c_size_t,
                                                    C.POINTER(vp), C.c_int, C.POINTER(vp)]),
         "pcs_b200_enable_peer": (C.c_int, [vp, C.c_int]),
+        "pcs_b200_ipc_export": (C.c_int, [vp, vp, C.POINTER(IpcHandle)]),
+        "pcs_b200_ipc_open": (C.c_int, [vp, C.POINTER(IpcHandle), C.POINTER(vp)]),
+        "pcs_b200_ipc_close": (C.c_int, [vp, vp]),
         "pcs_b200_batch_run": (C.c_int, [vp, vp, vp]),
         "pcs_b200_batch_destroy": (None, [vp, vp]),
         "pcs_b200_batch_launches": (C.c_int, [vp]),
@@ -293,6 +300,21 @@ class Context:
     def enable_peer(self, peer_device):
         """Single-process multi-GPU: let this context's kernels touch cudaMalloc memory of peer_device."""
         self._check(lib.pcs_b200_enable_peer(self.handle, peer_device))
+
+    def ipc_export(self, dev_ptr):
+        """bytes (80) that another process passes to ``ipc_open`` to map this device memory."""
+        h = IpcHandle()
+        self._check(lib.pcs_b200_ipc_export(self.handle, dev_ptr, C.byref(h)))
+        return bytes(h)
+
+    def ipc_open(self, handle_bytes):
+        h = IpcHandle.from_buffer_copy(handle_bytes)
+        p = C.c_void_p()
+        self._check(lib.pcs_b200_ipc_open(self.handle, C.byref(h), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, dev_ptr):
+        self._check(lib.pcs_b200_ipc_close(self.handle, dev_ptr))
 
     def pack_from_vertices_dev(self, stream, xyz_ptr, uv_ptr, n, color_ptr, payload_ptr, count_ptr=None,
                                cuda_stream=0):

@@ -95,6 +95,10 @@ struct pcs_ctx {
     size_t cap_stitch_in = 0, cap_stitch_out = 0;
     VoxelScratch voxel;
     StitchSlot stitch_slots[PCS_B200_STITCH_SLOTS];
+    // peer allocations mapped with pcs_b200_ipc_open (an allocation can be opened once per process)
+    struct IpcMap { uint8_t handle[64]; void *base; int refs; };
+    std::vector<IpcMap> ipc;
+    std::mutex ipc_mu;
 };
 
 struct pcs_batch {
@@ -375,6 +379,7 @@ void pcs_b200_destroy(pcs_ctx *ctx) {
     cudaFree(ctx->d_stitch_in);
     cudaFree(ctx->d_stitch_out);
     voxel_free(ctx->voxel);
+    for (auto &m : ctx->ipc) cudaIpcCloseMemHandle(m.base);
     for (StitchSlot &sl : ctx->stitch_slots) {
         if (sl.cs) { cudaStreamSynchronize(sl.cs); cudaStreamDestroy(sl.cs); }
         for (auto *p : sl.d_z) cudaFree(p);
@@ -739,6 +744,71 @@ int pcs_b200_enable_peer(pcs_ctx *ctx, int peer_device) {
     return PCS_OK;
 }
 
+// ---- one process per GPU: CUDA IPC --------------------------------------------------------------
+int pcs_b200_ipc_export(pcs_ctx *ctx, const void *dev_ptr, pcs_ipc_handle *out) {
+    if (!ctx || !dev_ptr || !out) return fail(ctx, PCS_ERR_INVALID, "null argument");
+    DeviceGuard dg_(ctx->device);
+    // the handle names the whole allocation: find its base (driver API through the runtime's entry point table)
+    typedef int (*get_range_t)(unsigned long long *, size_t *, unsigned long long);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
+        cudaGetLastError();
+        return fail(ctx, PCS_ERR_CUDA, "cuMemGetAddressRange is not available");
+    }
+    unsigned long long base = 0;
+    size_t bytes = 0;
+    if (reinterpret_cast<get_range_t>(fn)(&base, &bytes, (unsigned long long)reinterpret_cast<uintptr_t>(dev_ptr)) != 0)
+        return fail(ctx, PCS_ERR_INVALID, "not a device allocation of this process");
+    cudaIpcMemHandle_t h;
+    CU(ctx, cudaIpcGetMemHandle(&h, reinterpret_cast<void *>(static_cast<uintptr_t>(base))));
+    static_assert(sizeof h == sizeof out->reserved, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out->reserved, &h, sizeof h);
+    out->offset = (uint64_t)(reinterpret_cast<uintptr_t>(dev_ptr) - (uintptr_t)base);
+    out->device = (uint64_t)ctx->device;
+    return PCS_OK;
+}
+
+int pcs_b200_ipc_open(pcs_ctx *ctx, const pcs_ipc_handle *handle, void **dev_ptr_out) {
+    if (!ctx || !handle || !dev_ptr_out) return fail(ctx, PCS_ERR_INVALID, "null argument");
+    *dev_ptr_out = nullptr;
+    DeviceGuard dg_(ctx->device);
+    std::lock_guard<std::mutex> lk(ctx->ipc_mu);
+    for (auto &m : ctx->ipc)
+        if (memcmp(m.handle, handle->reserved, 64) == 0) {
+            ++m.refs;
+            *dev_ptr_out = static_cast<uint8_t *>(m.base) + handle->offset;
+            return PCS_OK;
+        }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle->reserved, sizeof h);
+    void *base = nullptr;
+    CU(ctx, cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    pcs_ctx::IpcMap m;
+    memcpy(m.handle, handle->reserved, 64);
+    m.base = base;
+    m.refs = 1;
+    ctx->ipc.push_back(m);
+    *dev_ptr_out = static_cast<uint8_t *>(base) + handle->offset;
+    return PCS_OK;
+}
+
+int pcs_b200_ipc_close(pcs_ctx *ctx, void *dev_ptr) {
+    if (!ctx || !dev_ptr) return fail(ctx, PCS_ERR_INVALID, "null argument");
+    DeviceGuard dg_(ctx->device);
+    std::lock_guard<std::mutex> lk(ctx->ipc_mu);
+    // the mapping that contains dev_ptr: the one with the largest base not above it
+    int best = -1;
+    for (size_t i = 0; i < ctx->ipc.size(); ++i)
+        if (ctx->ipc[i].base <= dev_ptr && (best < 0 || ctx->ipc[i].base > ctx->ipc[best].base)) best = (int)i;
+    if (best < 0) return fail(ctx, PCS_ERR_INVALID, "pointer was not returned by pcs_b200_ipc_open");
+    if (--ctx->ipc[best].refs == 0) {
+        CU(ctx, cudaIpcCloseMemHandle(ctx->ipc[best].base));
+        ctx->ipc.erase(ctx->ipc.begin() + best);
+    }
+    return PCS_OK;
+}
+
 int pcs_b200_batch_run(pcs_ctx *ctx, pcs_batch *b, void *cuda_stream) {
     if (!ctx || !b) return fail(ctx, PCS_ERR_INVALID, "null argument");
     cudaStream_t cs = (cudaStream_t)cuda_stream;
@@ -1048,10 +1118,10 @@ static int voxel_args_ok(pcs_ctx *ctx, const int16_t *records_dev, int n, int le
     if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
     if (n < 0 || leaf_mm < 1 || leaf_mm > 32767 || (n && (!records_dev || !out)))
         return fail(ctx, PCS_ERR_INVALID, "bad voxel-merge arguments");
-    // the per-voxel sums are uint32 (oracle/SPEC.md s3): 255 * n and (leaf - 1) * n must fit, with
-    // room for one more count (the mean's +-1 fix-up works modulo 2^32)
-    if ((long long)n * 256 > 0xFFFFFFFFll || (long long)n * leaf_mm > 0xFFFFFFFFll)
-        return fail(ctx, PCS_ERR_UNSUPPORTED, "voxel merge: n * max(256, leaf_mm) must stay below 2^32");
+    // n * 10 bytes is what the reference's int32 size header can describe (src/pcs-multicamera-client.cpp:394);
+    // the sort-based variants have tighter limits of their own (voxel_run)
+    if ((long long)n * 10 > 0x7FFFFFFFll)
+        return fail(ctx, PCS_ERR_UNSUPPORTED, "voxel merge: n * 10 bytes must fit the int32 size header");
     return PCS_OK;
 }
 
@@ -1060,30 +1130,37 @@ static int voxel_fail(pcs_ctx *ctx, int rc) {
                 "voxel merge failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
 }
 
-// voxel_variant: 0 = auto (MSD partition + bitmap ranking when the cloud fits its limits, else the one-sweep
-// sort when the (key, index) word fits 64 bits, else the pair sort), 1 = pair sort, 2 / 3 = one-sweep sort with
-// 8- / 10-bit digits, 4 = MSD only
+// voxel_variant: 0 = auto: the one-sweep sort when the (key, index) word fits 64 bits and the uint32 sums can
+// hold n points, else the slab partition + bitmap ranking (no limit on n), else the pair sort; 1 = pair sort,
+// 2 / 3 = one-sweep sort with 8- / 10-bit digits, 4 = slab partition + bitmap ranking only
+static int voxel_run_msd(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, int16_t *out_dev, cudaStream_t cs,
+                         bool slab, int kz_lo, int kz_hi) {
+    int32_t *nv_dev = nullptr;
+    int rc = voxel_merge_msd(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, slab, kz_lo, kz_hi, &nv_dev);
+    if (rc != 0) return rc;
+    if (cudaMemcpyAsync(ctx->voxel.h_count, nv_dev, 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
+        cudaStreamSynchronize(cs) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+        return -2;
+    const int nv = ctx->voxel.h_count[0];
+    return (nv < 0 || nv > n) ? -2 : nv;
+}
+
 static int voxel_run(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, int16_t *out_dev, cudaStream_t cs,
                      bool slab, int kz_lo, int kz_hi) {
     const int vv = ctx->voxel_variant;
+    if (vv == 4) return voxel_run_msd(ctx, records_dev, n, leaf_mm, out_dev, cs, slab, kz_lo, kz_hi);
+    // the sort-based variants keep uint32 per-voxel sums (oracle/SPEC.md s3): 255 * n and (leaf - 1) * n must fit,
+    // with room for one more count (the mean's +-1 fix-up works modulo 2^32)
+    const bool sums_fit = (long long)n * 256 <= 0xFFFFFFFFll && (long long)n * leaf_mm <= 0xFFFFFFFFll;
     int rc = -4;
-    if (vv == 0 || vv == 4) {
-        int32_t *nv_dev = nullptr;
-        rc = voxel_merge_msd(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, slab, kz_lo, kz_hi, &nv_dev);
-        if (rc == 0) {
-            if (cudaMemcpyAsync(ctx->voxel.h_count, nv_dev, 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
-                cudaStreamSynchronize(cs) != cudaSuccess || cudaGetLastError() != cudaSuccess)
-                return -2;
-            const int nv = ctx->voxel.h_count[0];
-            return (nv < 0 || nv > n) ? -2 : nv;
-        }
-        if (vv == 4 || rc != -4) return rc;
+    if (sums_fit) {
+        if (vv == 3)
+            rc = voxel_merge_sweep<10, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, slab, kz_lo, kz_hi);
+        else if (vv == 0 || vv == 2 || slab)
+            rc = voxel_merge_sweep<8, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, slab, kz_lo, kz_hi);
     }
-    if (vv == 3)
-        rc = voxel_merge_sweep<10, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, slab, kz_lo, kz_hi);
-    else if (vv == 0 || vv == 2 || slab)
-        rc = voxel_merge_sweep<8, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, slab, kz_lo, kz_hi);
-    if (!slab && (vv == 1 || (vv == 0 && rc == -4)))
+    if (vv == 0 && rc == -4) rc = voxel_run_msd(ctx, records_dev, n, leaf_mm, out_dev, cs, slab, kz_lo, kz_hi);
+    if (sums_fit && !slab && (vv == 1 || (vv == 0 && rc == -4)))
         rc = voxel_merge(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs);
     return rc;
 }
@@ -1128,21 +1205,31 @@ int pcs_b200_voxel_merge(pcs_ctx *ctx, const int16_t *records_host, int n, int l
     if (n < 0 || (n && (!records_host || !out_host))) return fail(ctx, PCS_ERR_INVALID, "bad arguments");
     if (n == 0) return 0;
     DeviceGuard dg_(ctx->device);
-    int16_t *d_in = nullptr, *d_out = nullptr;
-    if (cudaMalloc(&d_in, (size_t)n * 10 + 64) != cudaSuccess || cudaMalloc(&d_out, (size_t)n * 10 + 64) != cudaSuccess) {
-        cudaGetLastError();
-        cudaFree(d_in); cudaFree(d_out);
-        return fail(ctx, PCS_ERR_NOMEM, "cudaMalloc failed");
+    // device staging kept across calls (the stitch scratch: records in, voxels out)
+    const size_t bytes = (size_t)n * 10 + 64;
+    {
+        std::lock_guard<std::mutex> lk(ctx->scratch_mu);
+        if (bytes > ctx->cap_stitch_in) {
+            cudaFree(ctx->d_stitch_in);
+            ctx->d_stitch_in = nullptr; ctx->cap_stitch_in = 0;
+            if (cudaMalloc(&ctx->d_stitch_in, bytes) != cudaSuccess) { cudaGetLastError(); return fail(ctx, PCS_ERR_NOMEM, "cudaMalloc failed"); }
+            ctx->cap_stitch_in = bytes;
+        }
+        if (bytes > ctx->cap_stitch_out) {
+            cudaFree(ctx->d_stitch_out);
+            ctx->d_stitch_out = nullptr; ctx->cap_stitch_out = 0;
+            if (cudaMalloc(&ctx->d_stitch_out, bytes) != cudaSuccess) { cudaGetLastError(); return fail(ctx, PCS_ERR_NOMEM, "cudaMalloc failed"); }
+            ctx->cap_stitch_out = bytes;
+        }
     }
+    int16_t *d_in = reinterpret_cast<int16_t *>(ctx->d_stitch_in), *d_out = reinterpret_cast<int16_t *>(ctx->d_stitch_out);
     cudaStream_t cs = ctx->streams[0].cs;
-    int rc = PCS_ERR_CUDA;
-    if (cudaMemcpyAsync(d_in, records_host, (size_t)n * 10, cudaMemcpyHostToDevice, cs) == cudaSuccess) {
-        rc = pcs_b200_voxel_merge_dev(ctx, d_in, n, leaf_mm, d_out, cs);
-        if (rc > 0 && (cudaMemcpyAsync(out_host, d_out, (size_t)rc * 10, cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
-                       cudaStreamSynchronize(cs) != cudaSuccess))
-            rc = fail(ctx, PCS_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-    cudaFree(d_in); cudaFree(d_out);
+    if (cudaMemcpyAsync(d_in, records_host, (size_t)n * 10, cudaMemcpyHostToDevice, cs) != cudaSuccess)
+        return fail(ctx, PCS_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(cudaGetLastError()));
+    int rc = pcs_b200_voxel_merge_dev(ctx, d_in, n, leaf_mm, d_out, cs);
+    if (rc > 0 && (cudaMemcpyAsync(out_host, d_out, (size_t)rc * 10, cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
+                   cudaStreamSynchronize(cs) != cudaSuccess))
+        rc = fail(ctx, PCS_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(cudaGetLastError()));
     return rc;
 }
 

@@ -124,6 +124,13 @@ int main(int argc, char **argv) {
             ++sent;
         }
         printf("pcs_camera_node: %ld frames sent\n", sent);
+        // Half-close and drain: a push-mode camera never reads the stitcher's pulls, and close() with unread bytes
+        // in the receive queue resets the connection -- the peer would lose the frames it has not read yet.
+        shutdown(client, SHUT_WR);
+        timeval tv = {5, 0};
+        setsockopt(client, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
+        char drain[256];
+        while (recv(client, drain, sizeof drain, 0) > 0) {}
         close(client);
         close(srv);
     } catch (const std::exception &e) {

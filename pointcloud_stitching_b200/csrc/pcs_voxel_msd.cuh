@@ -36,7 +36,7 @@
 namespace pcs {
 
 constexpr int VM_LB = 14;            // a sub-bucket spans at most 2^VM_LB voxel keys (2 KB bitmap)
-constexpr int VM_F2 = 10;            // and a slab at most 2^VM_F2 sub-buckets
+constexpr int VM_F2 = 11;            // and a slab at most 2^VM_F2 sub-buckets
 constexpr int VM_MAX_SLABS = 1024;
 constexpr int VM_THREADS = 256, VM_ITEMS = 16, VM_TILE = VM_THREADS * VM_ITEMS;
 constexpr int VM_SPAN = 8;           // sub-buckets per local task
@@ -68,6 +68,7 @@ struct VmGeom {
     int n_slabs, dz;    // dz: z planes of the box
     int big;            // sub-buckets with more points go to the wide (CTA) path
     uint32_t m32;       // floor(2^32 / leaf) + 1: floor(u / leaf) = umulhi(u, m32) for u < 2^17 (0: leaf == 1)
+    float rdx, rdy;     // 1 / dx, 1 / dy (vm_unkey)
 };
 
 // floor((v + bias) / leaf) with one 32-bit multiply-high.  m32 * leaf = 2^32 + e, 0 < e <= leaf, so the
@@ -252,12 +253,27 @@ vm_l2(const uint64_t *__restrict__ in, VmGeom vg, const VmSlab *__restrict__ sla
 }
 
 // ---- 5. the local stage ---------------------------------------------------------------------------
-// One voxel record from its sums.  key = voxel key inside the slab.
-__device__ __forceinline__ void vm_record(uint16_t *o, uint64_t key, uint32_t zfirst, const uint32_t (&a)[6], uint32_t cnt,
-                                          const SweepGeom &g) {
-    const uint64_t t = g.mdx ? __umul64hi(key, g.mdx) : key;           // key / dx
-    const uint64_t u = g.mdy ? __umul64hi(t, g.mdy) : t;               // key / (dx * dy)
-    const int qx = (int)(key - t * g.dx) + g.x0, qy = (int)(t - u * g.dy) + g.y0, qz = (int)u + (int)zfirst + g.z0;
+// key (inside the slab, < 2^24) -> voxel coordinates.  key / dx by float reciprocal: (float)key is exact, the
+// product is off by far less than 1, a +-1 fix-up on the integer remainder makes it exact.
+__device__ __forceinline__ void vm_unkey(uint32_t key, uint32_t zfirst, const VmGeom &vg, int &qx, int &qy, int &qz) {
+    const SweepGeom &g = vg.g;
+    uint32_t t = (uint32_t)__float2int_rz(__fmul_rn((float)key, vg.rdx));
+    int rx = (int)(key - t * g.dx);
+    if (rx < 0) { --t; rx += (int)g.dx; } else if ((uint32_t)rx >= g.dx) { ++t; rx -= (int)g.dx; }
+    uint32_t u = (uint32_t)__float2int_rz(__fmul_rn((float)t, vg.rdy));
+    int ry = (int)(t - u * g.dy);
+    if (ry < 0) { --u; ry += (int)g.dy; } else if ((uint32_t)ry >= g.dy) { ++u; ry -= (int)g.dy; }
+    qx = rx + g.x0;
+    qy = ry + g.y0;
+    qz = (int)u + (int)zfirst + g.z0;
+}
+
+// One voxel record from its sums.
+__device__ __forceinline__ void vm_record(uint16_t *o, uint32_t key, uint32_t zfirst, const uint32_t (&a)[6], uint32_t cnt,
+                                          const VmGeom &vg) {
+    const SweepGeom &g = vg.g;
+    int qx, qy, qz;
+    vm_unkey(key, zfirst, vg, qx, qy, qz);
     const float r = __frcp_rn((float)cnt);
     uint32_t q[6];
 #pragma unroll
@@ -276,10 +292,10 @@ __device__ __forceinline__ void vm_record(uint16_t *o, uint64_t key, uint32_t zf
 }
 
 // wide version: sums up to 2^28 points (colour sums as 4-bit halves), exact 64-bit division
-__device__ __forceinline__ void vm_record_wide(uint16_t *o, uint64_t key, uint32_t zfirst, const uint32_t *a, const SweepGeom &g) {
-    const uint64_t t = g.mdx ? __umul64hi(key, g.mdx) : key;
-    const uint64_t u = g.mdy ? __umul64hi(t, g.mdy) : t;
-    const int qx = (int)(key - t * g.dx) + g.x0, qy = (int)(t - u * g.dy) + g.y0, qz = (int)u + (int)zfirst + g.z0;
+__device__ __forceinline__ void vm_record_wide(uint16_t *o, uint32_t key, uint32_t zfirst, const uint32_t *a, const VmGeom &vg) {
+    const SweepGeom &g = vg.g;
+    int qx, qy, qz;
+    vm_unkey(key, zfirst, vg, qx, qy, qz);
     const uint64_t cnt = a[9];
     const uint32_t mx = (uint32_t)((uint64_t)a[0] / cnt), my = (uint32_t)((uint64_t)a[1] / cnt), mz = (uint32_t)((uint64_t)a[2] / cnt);
     const uint32_t r = (uint32_t)((16ull * a[3] + a[4]) / cnt), gg = (uint32_t)((16ull * a[5] + a[6]) / cnt),
@@ -297,6 +313,7 @@ struct VmWarpSmem {
     uint32_t bm[VM_BM_WORDS];
     uint16_t pre[VM_BM_WORDS];
     uint32_t acc[VM_SLOTS * 5];     // a slot's record (10 B) overwrites the start of its own sums (20 B)
+    uint16_t skey[VM_SLOTS];        // the key (inside the sub-bucket) of every slot of the round
 };
 struct VmBigSmem {
     uint32_t bm[VM_BM_WORDS];
@@ -399,9 +416,9 @@ vm_local(const uint64_t *__restrict__ in, VmGeom vg, const VmSlab *__restrict__ 
                         const int bit = __ffs(bits) - 1;
                         bits &= bits - 1;
                         if (slot < cntr) {
-                            const uint64_t key = ((uint64_t)d2 << sl.shift) | (uint32_t)(wd * 32 + bit);
+                            const uint32_t key = (d2 << sl.shift) | (uint32_t)(wd * 32 + bit);
                             uint16_t r[5];
-                            vm_record_wide(r, key, sl.zfirst, b.acc + slot * 10, g);
+                            vm_record_wide(r, key, sl.zfirst, b.acc + slot * 10, vg);
                             uint16_t *o = stage + 5 * ((size_t)beg + lo + slot);
 #pragma unroll
                             for (int q = 0; q < 5; ++q) o[q] = r[q];
@@ -419,6 +436,8 @@ vm_local(const uint64_t *__restrict__ in, VmGeom vg, const VmSlab *__restrict__ 
     // ---- warp path
     VmWarpSmem &ws = sm.w[warp];
     const int wid = ((int)blockIdx.x - big_blocks) * VM_LWARPS + warp, nwarps = ((int)gridDim.x - big_blocks) * VM_LWARPS;
+    constexpr int CH = 8;                              // words per lane and chunk: 256 points are in flight at once
+    constexpr uint64_t NONE = ~0ull;                   // no word looks like this (bit 63 of a word is always 0)
     for (int ti = wid; ti < n_tasks; ti += nwarps) {
         const VmTask task = tasks[ti];
         const VmSlab sl = slabs[task.slab];
@@ -430,9 +449,21 @@ vm_local(const uint64_t *__restrict__ in, VmGeom vg, const VmSlab *__restrict__ 
             if (m == 0 || m > (uint32_t)vg.big) continue;         // empty: vout stays 0; big: the wide path writes it
             for (int k = lane; k < W; k += 32) ws.bm[k] = 0;
             __syncwarp();
-            for (uint32_t i = lane; i < m; i += 32) {
-                const uint32_t k = (uint32_t)(in[beg + i] >> vg.payb) & kmask;
-                if (!((ws.bm[k >> 5] >> (k & 31)) & 1u)) atomicOr(ws.bm + (k >> 5), 1u << (k & 31));
+            uint64_t w[CH];
+            // pass 1: which keys occur (a sub-bucket of <= 256 points stays in registers for pass 2)
+            for (uint32_t c0 = 0; c0 < m; c0 += 32 * CH) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const uint32_t i = c0 + j * 32 + lane;
+                    w[j] = i < m ? in[beg + i] : NONE;
+                }
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    if (w[j] != NONE) {
+                        const uint32_t k = (uint32_t)(w[j] >> vg.payb) & kmask;
+                        if (!((ws.bm[k >> 5] >> (k & 31)) & 1u)) atomicOr(ws.bm + (k >> 5), 1u << (k & 31));
+                    }
+                }
             }
             __syncwarp();
             // popcount prefix: lane l owns words [l * per, (l + 1) * per)
@@ -462,39 +493,40 @@ vm_local(const uint64_t *__restrict__ in, VmGeom vg, const VmSlab *__restrict__ 
                 const uint32_t cntr = min((uint32_t)VM_SLOTS, V - lo);
                 for (uint32_t k = lane; k < cntr * 5; k += 32) ws.acc[k] = 0;
                 __syncwarp();
-                for (uint32_t i = lane; i < m; i += 32) {
-                    const uint64_t w = in[beg + i];
-                    const uint32_t k = (uint32_t)(w >> vg.payb) & kmask;
-                    const uint32_t slot = (uint32_t)ws.pre[k >> 5] + __popc(ws.bm[k >> 5] & ((1u << (k & 31)) - 1u)) - lo;
-                    if (slot < cntr) {
-                        uint32_t *a = ws.acc + slot * 5;
-                        const uint32_t lo32 = (uint32_t)w, offs = (uint32_t)(w >> 24);
-                        atomicAdd(a + 0, (offs & om) | (((offs >> g.off_bits) & om) << 16));
-                        atomicAdd(a + 1, ((offs >> (2 * g.off_bits)) & om) | (1u << 16));
-                        atomicAdd(a + 2, lo32 & 0xFFu);
-                        atomicAdd(a + 3, (lo32 >> 8) & 0xFFu);
-                        atomicAdd(a + 4, (lo32 >> 16) & 0xFFu);
+                // pass 2: every point adds itself to its voxel's sums (rank = occupied keys below it)
+                for (uint32_t c0 = 0; c0 < m; c0 += 32 * CH) {
+                    if (m > 32 * CH) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            const uint32_t i = c0 + j * 32 + lane;
+                            w[j] = i < m ? in[beg + i] : NONE;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        if (w[j] != NONE) {
+                            const uint32_t k = (uint32_t)(w[j] >> vg.payb) & kmask;
+                            const uint32_t slot = (uint32_t)ws.pre[k >> 5] + __popc(ws.bm[k >> 5] & ((1u << (k & 31)) - 1u)) - lo;
+                            if (slot < cntr) {
+                                uint32_t *a = ws.acc + slot * 5;
+                                const uint32_t lo32 = (uint32_t)w[j], offs = (uint32_t)(w[j] >> 24);
+                                atomicAdd(a + 0, (offs & om) | (((offs >> g.off_bits) & om) << 16));
+                                atomicAdd(a + 1, ((offs >> (2 * g.off_bits)) & om) | (1u << 16));
+                                atomicAdd(a + 2, lo32 & 0xFFu);
+                                atomicAdd(a + 3, (lo32 >> 8) & 0xFFu);
+                                atomicAdd(a + 4, (lo32 >> 16) & 0xFFu);
+                                ws.skey[slot] = (uint16_t)k;      // every point of the voxel stores the same value
+                            }
+                        }
                     }
                 }
                 __syncwarp();
-                // every occupied key of the round -> its record (in shared memory, then out in one stream)
-                for (int k = 0; k < per; ++k) {
-                    const int wd = lane * per + k;
-                    if (wd < W) {
-                        uint32_t bits = ws.bm[wd], slot = (uint32_t)ws.pre[wd] - lo;
-                        while (bits) {
-                            const int bit = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            if (slot < cntr) {
-                                uint32_t *a = ws.acc + slot * 5;
-                                const uint32_t s[6] = {a[0] & 0xFFFFu, a[0] >> 16, a[1] & 0xFFFFu, a[2], a[3], a[4]};
-                                const uint32_t cnt = a[1] >> 16;
-                                const uint64_t key = ((uint64_t)d2 << sl.shift) | (uint32_t)(wd * 32 + bit);
-                                vm_record(reinterpret_cast<uint16_t *>(a), key, sl.zfirst, s, cnt, g);
-                            }
-                            ++slot;
-                        }
-                    }
+                // one lane per voxel: sums -> record, written over the voxel's own sums
+                for (uint32_t s_ = lane; s_ < cntr; s_ += 32) {
+                    uint32_t *a = ws.acc + s_ * 5;
+                    const uint32_t sums[6] = {a[0] & 0xFFFFu, a[0] >> 16, a[1] & 0xFFFFu, a[2], a[3], a[4]};
+                    const uint32_t cnt = a[1] >> 16;
+                    vm_record(reinterpret_cast<uint16_t *>(a), (d2 << sl.shift) | (uint32_t)ws.skey[s_], sl.zfirst, sums, cnt, vg);
                 }
                 __syncwarp();
                 uint16_t *o = stage + 5 * ((size_t)beg + lo);
@@ -548,11 +580,16 @@ struct VmPlan {
     long long m = 0;     // points inside the z range
 };
 
+inline int vm_avg() {       // tuning knob: average points per sub-bucket (PCS_VM_AVG)
+    static const int v = pipe_knob("PCS_VM_AVG", 32, 1, 4096);
+    return v;
+}
+
 // Slabs from the z histogram.  Returns false when the cloud does not fit this path's limits.
 inline bool vm_make_plan(const SweepGeom &g, const uint32_t *zhist, int z0, int dz, VmPlan &p) {
     const unsigned long long plane = (unsigned long long)g.dx * g.dy;
-    if (plane > (1ull << (VM_LB + VM_F2))) return false;
-    const int pmax = (int)std::max<unsigned long long>(1, (1ull << (VM_LB + VM_F2)) / plane);
+    if (plane > (1ull << 24)) return false;                  // a slab's keys are 24 bits (float-exact, 32-bit arithmetic)
+    const int pmax = (int)std::max<unsigned long long>(1, (1ull << 24) / plane);
     long long m = 0;
     for (int k = 0; k < dz; ++k)
         if (z0 + k >= g.z_lo && z0 + k < g.z_hi) m += zhist[z0 + k];
@@ -576,9 +613,12 @@ inline bool vm_make_plan(const SweepGeom &g, const uint32_t *zhist, int z0, int 
         planes = last_occupied;                                  // no trailing empty planes
         if ((int)p.slabs.size() >= VM_MAX_SLABS) return false;
         const unsigned long long range = (unsigned long long)planes * plane;
-        // ~256 points per sub-bucket, at least 128 keys, at most 2^VM_LB keys and 2^VM_F2 sub-buckets
+        // Sub-bucket width: a scan's points sit on surfaces, so most of a slab's key range is empty and the occupied
+        // sub-buckets hold several times the average -- aim at VM_AVG points per sub-bucket over the whole range
+        // (occupied ones then hold ~100-400, what one warp handles well); at least 128 keys, at most 2^VM_LB keys
+        // and 2^VM_F2 sub-buckets
         int shift = 7;
-        while (shift < VM_LB && ((range >> shift) > (1ull << VM_F2) || (double)cnt * (double)(1ull << shift) < 256.0 * (double)range)) ++shift;
+        while (shift < VM_LB && ((range >> shift) > (1ull << VM_F2) || (double)cnt * (double)(1ull << shift) < (double)vm_avg() * (double)range)) ++shift;
         if ((range + (1ull << shift) - 1) >> shift > (1ull << VM_F2)) return false;
         VmSlab s{};
         s.base = base;
@@ -676,6 +716,8 @@ inline int voxel_merge_msd(VoxelScratch &s, const int16_t *rec, int n, int leaf,
     // the packed accumulators count to 65535 and hold offset sums up to 65535; above ~1000 points one warp is
     // too slow anyway (a sub-bucket that large is mostly repeats of a few voxels: same-address atomics)
     vg.big = std::min(1024, 65535 / std::max(1, leaf - 1));
+    vg.rdx = 1.0f / (float)g.dx;
+    vg.rdy = 1.0f / (float)g.dy;
     vg.m32 = leaf == 1 ? 0u : (uint32_t)((1ull << 32) / (unsigned long long)leaf) + 1u;
     // tables: one upload
     uint8_t *ht = s.h_tab;

@@ -69,6 +69,40 @@ def test_multigpu_cxx_host_bit_exact_on_gpu():
     assert r.stdout.strip().endswith("OK")
 
 
+MP_BIN = os.path.join(ROOT, "tests", "cpp", "_build", "multiproc_pull_main")
+
+
+def _build_multiproc():
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cuda = os.path.dirname(os.path.dirname(os.path.realpath(nvcc)))
+    os.makedirs(os.path.dirname(MP_BIN), exist_ok=True)
+    cmd = ["/usr/bin/g++", "-std=c++11", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(ROOT, "oracle"), "-I" + os.path.join(cuda, "include"),
+           os.path.join(ROOT, "tests", "cpp", "multiproc_pull_main.cpp"), "-o", MP_BIN,
+           pcs.LIB_PATH, os.path.join(ROOT, "oracle", "_build", "libpcs_oracle.so"),
+           "-L" + os.path.join(cuda, "lib64"), "-lcudart",
+           "-Wl,-rpath," + os.path.dirname(pcs.LIB_PATH), "-Wl,-rpath," + os.path.join(ROOT, "oracle", "_build"),
+           "-Wl,-rpath," + os.path.join(cuda, "lib64")]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+
+
+def test_multiprocess_cxx_host_compiles_and_links():
+    """tests/cpp/multiproc_pull_main.cpp: one PROCESS per GPU (fork + socketpair, no torch / NCCL), the peers'
+    frames mapped with pcs_b200_ipc_export / pcs_b200_ipc_open, pull exchange through the C ABI."""
+    _build_multiproc()
+    assert os.path.exists(MP_BIN)
+
+
+@pytest.mark.gpu
+def test_multiprocess_cxx_host_bit_exact_on_gpu():
+    """Runs on two GPUs when the box has them (prints SKIP and passes on one)."""
+    _build_multiproc()
+    r = subprocess.run([MP_BIN], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("OK"), r.stdout
+
+
 def test_division_by_constant_is_correctly_rounded():
     """The pipelined kernel divides by the colour width with a precomputed reciprocal and two
     Markstein corrections; check it against IEEE division over 2^-12..2^24 for common widths."""

@@ -174,8 +174,8 @@ def test_stitch_errors(ctx):
 
 @pytest.fixture(scope="module", params=[0, 1, 2, 3, 4], ids=["auto", "pair_sort", "sweep8", "sweep10", "msd"])
 def vctx(request):
-    """One context per voxel_variant: auto (MSD partition + bitmap ranking, falling back to the sorts), the
-    (key, index) pair sort, the one-sweep sort (8 / 10 bit), MSD only."""
+    """One context per voxel_variant: auto (the one-sweep sort, falling back to the slab partition / the pair sort), the
+    (key, index) pair sort, the one-sweep sort (8 / 10 bit), slab partition + bitmap ranking only."""
     c = pcs.Context(device=0, max_streams=2, voxel_variant=request.param)
     c.variant = request.param
     yield c
@@ -386,4 +386,23 @@ def test_voxel_merge_msd_shapes(R):
     rec[:, 2] = 0
     rec[-1, :3] = (30000, 30000, 3000)        # stretches the box
     check(rec, 10)
+    c.close()
+
+
+def test_voxel_merge_beyond_the_uint32_sum_limit(R):
+    """20 cameras x 1280x720 = 18.4 M points: 255 * n no longer fits the uint32 colour sums of the sort-based
+    variants; auto then takes the slab-partition variant, which counts colours as two 4-bit halves where a voxel is
+    that crowded."""
+    c = pcs.Context(device=0, max_streams=1)
+    rng = np.random.default_rng(31)
+    n = 20 * 921600
+    rec = random_records(rng, n)
+    rec[:, :3] = (rng.normal(0, 1200, (n, 3))).clip(-32000, 32000).astype(np.int16)
+    rec[: n // 2, :3] = (40, -7, 1999)            # 9.2 M points in one voxel: its colour sums pass 2^31
+    d = torch.from_numpy(rec.reshape(-1)).cuda()
+    out = torch.zeros(n * 5, dtype=torch.int16, device="cuda")
+    nv = c.voxel_merge_dev(d.data_ptr(), n, 10, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = R.voxel_merge(rec, 10)
+    assert nv == len(want) and np.array_equal(out[: nv * 5].cpu().numpy().reshape(-1, 5), want)
     c.close()

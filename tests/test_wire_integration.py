@@ -265,6 +265,7 @@ def test_stitch_node_serves_the_viewer(restatement, tmp_path, mode):
                                        "right": np.asarray(tfs[1], np.float64).reshape(4, 4).tolist()}))
         sargs += ["--pcl", "--tf-file", str(tf_file), "--names", "left,right"]
     stitcher = subprocess.Popen(sargs, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    problem = None
     try:
         v = _connect(viewer_port)
         for f in range(served):
@@ -275,9 +276,15 @@ def test_stitch_node_serves_the_viewer(restatement, tmp_path, mode):
                 want = restatement.pcl_stitch(pays, tfs, d)
             else:
                 want = restatement.concat([p.reshape(-1) for p in pays], d)
-            assert np.array_equal(got, np.frombuffer(want[4:].tobytes(), np.int16)), "stitched frame %d (%s)" % (f, mode)
+            if not np.array_equal(got, np.frombuffer(want[4:].tobytes(), np.int16)):
+                problem = "stitched frame %d differs (%s)" % (f, mode)
+                break
         v.close()
+    except (EOFError, OSError, RuntimeError) as e:
+        problem = repr(e)
     finally:
         sout = _finish(stitcher, "stitcher")
         outs = [_finish(n, "camera") for n in nodes]
-    assert "%d stitched frames served" % served in sout, sout + "".join(outs)
+    log = "\n--- stitcher ---\n" + sout + "".join("\n--- camera %d ---\n%s" % (i, o) for i, o in enumerate(outs))
+    assert problem is None, problem + log
+    assert "%d stitched frames served" % served in sout, log

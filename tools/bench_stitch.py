@@ -76,8 +76,8 @@ def main():
     out = torch.zeros(total * 5, dtype=torch.int16, device="cuda")
     nv = [0]
 
-    # voxel_variant: 0 auto (MSD partition + bitmap ranking), 1 (key, index) pair sort, 2 / 3 one-sweep sort with
-    # 8- / 10-bit digits, 4 MSD only
+    # voxel_variant: 0 auto (one-sweep sort), 1 (key, index) pair sort, 2 / 3 one-sweep sort with 8- / 10-bit digits,
+    # 4 slab partition + bitmap ranking
     for variant, name in ((0, "voxel_merge_10mm"), (1, "voxel_merge_10mm_pair_sort"), (2, "voxel_merge_10mm_sweep8"),
                           (3, "voxel_merge_10mm_sweep10"), (4, "voxel_merge_10mm_msd")):
         if a.only_voxel_variant >= 0 and variant != a.only_voxel_variant:
