@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--configs", default="c3,c5", help="extra BASELINE configs measured into the same line ('none' to skip)")
     ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the sustained K1 leg (0 to skip)")
     ap.add_argument("--e2e-slots", type=int, default=3, choices=[1, 2, 3, 4], help="stitched frames in flight in the e2e leg")
+    ap.add_argument("--merge-lanes", type=int, default=4, help="c3 / c5 at N = 1: stitched frames merged concurrently")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the stitched-bytes verification")
@@ -359,6 +360,7 @@ def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, worl
             batches.append(ctx.batch(jobs))
     outs = [torch.zeros(n * 5, dtype=torch.int16, device=dev) for _ in range(frames)]
     nv = [0] * frames
+    counts = torch.zeros(frames, dtype=torch.int32, device=dev)
 
     def k1_only():
         for f in range(frames):
@@ -366,7 +368,25 @@ def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, worl
         if fset is not None:
             fset.barrier()
 
+    # world == 1: enqueue-only merges (box, key layout, pass count and voxel count stay on the device; the counts are
+    # read once, after the step's last frame) on `lanes` CUDA streams, one merge context (scratch + plan slot) each:
+    # consecutive stitched frames are merged concurrently, which fills the latency-bound phases of the sort
+    lanes = args.merge_lanes if world == 1 else 1
+    mctx = [ctx] + [pcs.Context(device=local, max_streams=1) for _ in range(lanes - 1)]
+    mstreams = [torch.cuda.current_stream()] + [torch.cuda.Stream() for _ in range(lanes - 1)]
+
     def merge_only():
+        if world == 1:
+            main = mstreams[0]
+            for s2 in mstreams[1:]:
+                s2.wait_stream(main)              # the frames' records (K1) are complete on the main stream
+            for f in range(frames):
+                k = f % lanes
+                mctx[k].voxel_merge_async_dev(stitched[f].payload.data_ptr(), n, LEAF_MM, outs[f].data_ptr(),
+                                              counts.data_ptr() + 4 * f, mstreams[k].cuda_stream)
+            for s2 in mstreams[1:]:
+                main.wait_stream(s2)
+            return
         for f in range(frames):
             total, mine = multigpu.sharded_voxel_merge(ctx, stitched[f].payload.data_ptr(), n, LEAF_MM, rank, world,
                                                        outs[f], cs, gather=False)
@@ -380,6 +400,10 @@ def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, worl
     ms_step = timer.run(step, iters)
     ms_k1 = timer.run(k1_only, iters)
     ms_merge = timer.run(merge_only, iters)
+    if world == 1:
+        nv = [int(v) for v in counts.cpu().tolist()]
+        if min(nv) < 0:
+            raise RuntimeError("voxel merge reported status %d" % min(nv))
     # voxels over all ranks (each rank keeps its z-slab of the grid)
     nv_local = torch.tensor([float(sum(nv))], device=dev, dtype=torch.float64)
     if world > 1:
@@ -394,6 +418,7 @@ def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, worl
            "n_gpus": world, "points_per_step": pts_step, "voxels_per_step": nv_total,
            "value": pts_step / (ms_step * 1e-3) / 1e6, "unit": "Mpoints/s", "ms_per_step": ms_step,
            "k1_ms_per_step": ms_k1, "merge_ms_per_step": ms_merge, "merge_ms_per_frame": ms_merge / frames,
+           "merge_lanes": lanes,
            "gpu_launches_per_step": None,
            "roofline": {"bound": "hbm", "kernel": "voxel merge (sw_keys_hist + sw_pass x P + sw_reduce; sw_pass dominant)",
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -439,6 +464,8 @@ def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, worl
     res["check"] = check
     for b in batches:
         b.close()
+    for c in mctx[1:]:
+        c.close()
     ctx.close()
     return res
 

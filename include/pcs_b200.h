@@ -265,11 +265,23 @@ PCS_API int pcs_b200_stitch_frames(pcs_ctx *ctx, int n_cams, const int32_t *stre
  * n * max(256, leaf_mm) < 2^32 (uint32 sums: 16.7 M points at the 10 mm leaf); larger clouds, up to what
  * the reference's int32 size header can describe (n * 10 < 2^31), take the slab-partition variant when
  * leaf <= 32 mm and a z plane of the occupied box holds <= 2^24 voxels (40 m x 40 m at the 10 mm leaf).
- * The call synchronises cuda_stream (the voxel count has to reach the host). */
+ * The call synchronises cuda_stream once, at the end (the voxel count has to reach the host). */
 PCS_API int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
                              int16_t *out_dev, void *cuda_stream);
 PCS_API int pcs_b200_voxel_merge(pcs_ctx *ctx, const int16_t *records_host, int n, int leaf_mm,
                          int16_t *out_host);
+
+/* Enqueue-only forms of the merge (the one-sweep sort, voxel_variant 0 / 2 / 3): the occupied box, the key
+ * layout, the number of sort passes and the voxel count all stay on the device, so a frame loop can queue
+ * K1 + merge for many frames and synchronise once.  *count_dev (device int32) receives the voxel count, or
+ * a negative pcs_status (PCS_ERR_UNSUPPORTED: the cloud's (key, index) word does not fit 64 bits -- use the
+ * synchronous call, which falls back).  Merges of one context share scratch memory: queue them on ONE
+ * stream.  Returns PCS_OK or a negative pcs_status. */
+PCS_API int pcs_b200_voxel_merge_async_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
+                                   int16_t *out_dev, int32_t *count_dev, void *cuda_stream);
+PCS_API int pcs_b200_voxel_merge_slab_async_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
+                                        int kz_lo, int kz_hi, int16_t *out_dev, int32_t *count_dev,
+                                        void *cuda_stream);
 
 /* Sharded voxel merge (multi-GPU: SURVEY s8(e) "sharded by voxel-key range").  The grid is cut
  * along z into n_slabs slabs of nearly equal population: slab r holds the points with

@@ -141,6 +141,8 @@ def _load():
         "pcs_b200_stitch_frames": (C.c_int, [vp, C.c_int, i32p, C.POINTER(vp), C.POINTER(vp), C.c_int, vp, C.c_size_t]),
         "pcs_b200_voxel_merge_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
         "pcs_b200_voxel_merge": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
+        "pcs_b200_voxel_merge_async_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp]),
+        "pcs_b200_voxel_merge_slab_async_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
         "pcs_b200_voxel_slab_plan_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, i32p, i32p, vp]),
         "pcs_b200_voxel_merge_slab_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         "pcs_b200_cloud_to_ply_rows_dev": (C.c_int, [vp, vp, C.c_int, vp, vp]),
@@ -398,6 +400,15 @@ class Context:
     def voxel_merge_dev(self, records_ptr, n, leaf_mm, out_ptr, cuda_stream=0):
         return self._check(lib.pcs_b200_voxel_merge_dev(self.handle, records_ptr, n, leaf_mm, out_ptr,
                                                         cuda_stream))
+
+    def voxel_merge_async_dev(self, records_ptr, n, leaf_mm, out_ptr, count_ptr, cuda_stream=0):
+        """Enqueue only: the voxel count (or a negative status) lands in the device int32 at count_ptr."""
+        self._check(lib.pcs_b200_voxel_merge_async_dev(self.handle, records_ptr, n, leaf_mm, out_ptr, count_ptr,
+                                                       cuda_stream))
+
+    def voxel_merge_slab_async_dev(self, records_ptr, n, leaf_mm, kz_lo, kz_hi, out_ptr, count_ptr, cuda_stream=0):
+        self._check(lib.pcs_b200_voxel_merge_slab_async_dev(self.handle, records_ptr, n, leaf_mm, kz_lo, kz_hi, out_ptr,
+                                                            count_ptr, cuda_stream))
 
     def voxel_slab_plan_dev(self, records_ptr, n, leaf_mm, n_slabs, cuda_stream=0):
         """(kz_splits[n_slabs + 1], slab_points[n_slabs]): equal-population cuts of the grid along z."""

@@ -85,6 +85,7 @@ struct pcs_ctx {
     int kernel_variant = 0;
     int voxel_variant = 0;
     int sm_count = 0;
+    int plan_slot = 0;      // this context's slot of the voxel sort's constant-memory plan
     StreamState *streams = nullptr;
     StreamParams *d_params = nullptr;
     std::mutex mu;          // guards `error`
@@ -340,6 +341,12 @@ int pcs_b200_create(const pcs_config *cfg, pcs_ctx **out) {
     ctx->kernel_variant = cfg->kernel_variant;
     ctx->voxel_variant = cfg->voxel_variant;
     ctx->sm_count = prop.multiProcessorCount;
+    {
+        static std::mutex slot_mu;
+        static int next_slot = 0;
+        std::lock_guard<std::mutex> lk(slot_mu);
+        ctx->plan_slot = next_slot++ % SW_PLAN_SLOTS;
+    }
     ctx->streams = new StreamState[cfg->max_streams];
     if (cudaMalloc(&ctx->d_params, sizeof(StreamParams) * cfg->max_streams) != cudaSuccess) {
         pcs_b200_destroy(ctx);
@@ -1155,9 +1162,9 @@ static int voxel_run(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_m
     int rc = -4;
     if (sums_fit) {
         if (vv == 3)
-            rc = voxel_merge_sweep<10, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, slab, kz_lo, kz_hi);
+            rc = voxel_merge_sweep<10, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, ctx->plan_slot, slab, kz_lo, kz_hi);
         else if (vv == 0 || vv == 2 || slab)
-            rc = voxel_merge_sweep<8, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, slab, kz_lo, kz_hi);
+            rc = voxel_merge_sweep<8, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, ctx->plan_slot, slab, kz_lo, kz_hi);
     }
     if (vv == 0 && rc == -4) rc = voxel_run_msd(ctx, records_dev, n, leaf_mm, out_dev, cs, slab, kz_lo, kz_hi);
     if (sums_fit && !slab && (vv == 1 || (vv == 0 && rc == -4)))
@@ -1174,6 +1181,44 @@ int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, in
     std::lock_guard<std::mutex> lk(ctx->scratch_mu);
     rc = voxel_run(ctx, records_dev, n, leaf_mm, out_dev, (cudaStream_t)cuda_stream, false, 0, 0);
     return rc < 0 ? voxel_fail(ctx, rc) : rc;
+}
+
+// Enqueue-only forms: nothing returns to the host; *count_dev = voxel count, or a negative pcs_status.
+static int voxel_async(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, int16_t *out_dev, int32_t *count_dev,
+                       cudaStream_t cs, bool slab, int kz_lo, int kz_hi) {
+    int rc = voxel_args_ok(ctx, records_dev, n, leaf_mm, out_dev);
+    if (rc) return rc;
+    if (!count_dev) return fail(ctx, PCS_ERR_INVALID, "count_dev must not be NULL");
+    if (ctx->voxel_variant != 0 && ctx->voxel_variant != 2 && ctx->voxel_variant != 3)
+        return fail(ctx, PCS_ERR_UNSUPPORTED, "the asynchronous merge is the one-sweep sort (voxel_variant 0, 2 or 3)");
+    if ((long long)n * 256 > 0xFFFFFFFFll || (long long)n * leaf_mm > 0xFFFFFFFFll)
+        return fail(ctx, PCS_ERR_UNSUPPORTED, "asynchronous voxel merge: n * max(256, leaf_mm) must stay below 2^32");
+    DeviceGuard dg_(ctx->device);
+    if (n == 0) {
+        CU(ctx, cudaMemsetAsync(count_dev, 0, 4, cs));
+        return PCS_OK;
+    }
+    std::lock_guard<std::mutex> lk(ctx->scratch_mu);
+    int32_t *nv_dev = nullptr;
+    if (ctx->voxel_variant == 3)
+        rc = voxel_merge_sweep_enqueue<10, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, ctx->plan_slot,
+                                                    slab, kz_lo, kz_hi, &nv_dev);
+    else
+        rc = voxel_merge_sweep_enqueue<8, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, ctx->plan_slot,
+                                                   slab, kz_lo, kz_hi, &nv_dev);
+    if (rc < 0) return voxel_fail(ctx, rc);
+    CU(ctx, cudaMemcpyAsync(count_dev, nv_dev, 4, cudaMemcpyDeviceToDevice, cs));
+    return PCS_OK;
+}
+
+int pcs_b200_voxel_merge_async_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, int16_t *out_dev,
+                                   int32_t *count_dev, void *cuda_stream) {
+    return voxel_async(ctx, records_dev, n, leaf_mm, out_dev, count_dev, (cudaStream_t)cuda_stream, false, 0, 0);
+}
+
+int pcs_b200_voxel_merge_slab_async_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, int kz_lo, int kz_hi,
+                                        int16_t *out_dev, int32_t *count_dev, void *cuda_stream) {
+    return voxel_async(ctx, records_dev, n, leaf_mm, out_dev, count_dev, (cudaStream_t)cuda_stream, true, kz_lo, kz_hi);
 }
 
 int pcs_b200_voxel_slab_plan_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, int n_slabs,

@@ -55,6 +55,20 @@ struct SweepGeom {
     int z_lo, z_hi;               // keep qz in [z_lo, z_hi)
 };
 
+// Everything the sort needs that depends on the data (the occupied box fixes the key layout): written by
+// sw_plan ON THE DEVICE and copied into a constant-memory slot, so that the merge needs no host round trip
+// and the kernels still read their geometry as constant-bank operands.  Launch grids are sized on the
+// host from upper bounds (n points, the widest possible key); blocks past the plan's counts exit.
+struct SweepPlan {
+    SweepGeom g;
+    int m;            // points to sort (== n without a slab filter)
+    int passes, n_tiles, n_chunks;
+    int status;       // 0, or -4 when the (key, slot) word does not fit 64 bits
+    int pad[3];
+};
+constexpr int SW_PLAN_SLOTS = 8;     // one per context (contexts sharing a slot must not merge concurrently)
+__constant__ SweepPlan c_sweep_plan[SW_PLAN_SLOTS];
+
 __device__ __forceinline__ uint32_t sw_q(int v, const SweepGeom &g) {
     return (uint32_t)(((unsigned long long)(uint32_t)(v + g.bias) * g.magic) >> 40);
 }
@@ -165,6 +179,47 @@ sw_bounds(const int16_t *__restrict__ rec, int n, SweepGeom g, uint32_t *__restr
         }
 }
 
+// ---- 0b. the plan -----------------------------------------------------------------------------
+__device__ __forceinline__ int sw_bits_for_dev(unsigned long long count) {     // bits for values 0 .. count-1 (>= 1)
+    int b = 1;
+    while (b < 63 && (1ull << b) < count) ++b;
+    return b;
+}
+__global__ void sw_plan(const uint32_t *__restrict__ bounds, SweepGeom base, int n, int slab, int tile, int bits,
+                        SweepPlan *__restrict__ plan, int32_t *__restrict__ nv_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    SweepPlan p;
+    p.g = base;
+    p.pad[0] = p.pad[1] = p.pad[2] = 0;
+    p.status = 0;
+    p.m = (int)bounds[6];
+    p.passes = p.n_tiles = p.n_chunks = 0;
+    if (p.m > 0 && p.m <= n) {
+        SweepGeom &g = p.g;
+        g.x0 = (int)bounds[0]; g.y0 = (int)bounds[1]; g.z0 = (int)bounds[2];
+        g.dx = bounds[3] - bounds[0] + 1;
+        g.dy = bounds[4] - bounds[1] + 1;
+        g.mdx = g.dx > 1 ? ~0ull / g.dx + 1ull : 0ull;
+        g.mdy = g.dy > 1 ? ~0ull / g.dy + 1ull : 0ull;
+        const unsigned long long dz = (unsigned long long)bounds[5] - bounds[2] + 1;
+        g.idx_bits = sw_bits_for_dev((unsigned long long)(slab ? p.m : n));
+        const int key_bits = sw_bits_for_dev((unsigned long long)g.dx * g.dy * dz);   // < 2^48 always
+        // the multiply-high divisions in sw_emit are exact while key * d stays below 2^64
+        const double vol = (double)g.dx * (double)g.dy * (double)dz * (double)max(g.dx, g.dy);
+        if (key_bits + g.idx_bits > 64 || vol >= 9.0e18) {
+            p.status = -4;
+        } else {
+            p.passes = (key_bits + bits - 1) / bits;
+            p.n_tiles = (p.m + tile - 1) / tile;
+            p.n_chunks = (p.m + SW_CHUNK - 1) / SW_CHUNK;
+        }
+    } else if (p.m > n) {
+        p.status = -2;
+    }
+    *plan = p;
+    if (p.status != 0 || p.m == 0) *nv_out = p.status;     // nothing else will write the result
+}
+
 // ---- 1. sort words, gather words and all digit histograms -------------------------------
 // pay[slot] = R | G<<8 | B<<16 | (x - leaf*kx) << 24 | (y - leaf*ky) << (24+ob) | (z - leaf*kz) << (24+2ob):
 // everything the reduce needs from a record in one aligned 8-byte load.  Without a slab filter a
@@ -173,10 +228,14 @@ sw_bounds(const int16_t *__restrict__ rec, int n, SweepGeom g, uint32_t *__restr
 // and the per-voxel sums are integers).
 template <int BITS, bool FILTER>
 __global__ void __launch_bounds__(SW_KH_THREADS)
-sw_keys_hist(const int16_t *__restrict__ rec, int n, SweepGeom g, int passes,
+sw_keys_hist(const int16_t *__restrict__ rec, int n, int plan_slot,
              uint64_t *__restrict__ words, uint64_t *__restrict__ pay, uint32_t *__restrict__ ghist,
              uint32_t *__restrict__ slot_counter) {
     constexpr int BINS = 1 << BITS;
+    const SweepPlan &plan = c_sweep_plan[plan_slot];
+    const SweepGeom &g = plan.g;
+    const int passes = plan.passes;
+    if (passes == 0) return;
     extern __shared__ uint32_t sw_hist[];    // [passes][BINS]
     __shared__ uint32_t warp_cnt[SW_KH_THREADS / 32], s_base;
     for (int k = threadIdx.x; k < passes * BINS; k += SW_KH_THREADS) sw_hist[k] = 0;
@@ -327,10 +386,13 @@ struct SweepPassCfg {
 // walk was most of the kernel.  One thread per digit, a step's loads issued together.
 template <int BITS, int THREADS, int ITEMS, bool BALLOT>
 __global__ void __launch_bounds__(THREADS, (BITS > 8 || THREADS > 256 ? 2 : (ITEMS <= 8 ? 4 : 3)))
-sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n, int shift,
+sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int plan_slot, int pass,
         const uint32_t *__restrict__ gbase, uint32_t *status, uint32_t *gstatus,
-        int n_tiles, uint32_t *ticket, uint32_t *err, int probe, int poll_ns) {
+        uint32_t *ticket, uint32_t *err, int probe, int poll_ns) {
     using Cfg = SweepPassCfg<BITS, THREADS, ITEMS>;
+    const SweepPlan &plan = c_sweep_plan[plan_slot];
+    if (pass >= plan.passes || (int)blockIdx.x >= plan.n_tiles) return;    // grids are sized for the worst case
+    const int n = plan.m, shift = plan.g.idx_bits + pass * BITS;
     constexpr int BINS = Cfg::BINS, WARPS = Cfg::WARPS, TILE = Cfg::TILE, DPT = Cfg::DPT;
     extern __shared__ __align__(16) uint8_t sw_smem[];
     uint64_t *skeys = reinterpret_cast<uint64_t *>(sw_smem);     // [TILE] the tile in digit order
@@ -534,7 +596,10 @@ sw_pass(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n, int 
 // ---- 4. voxel boundaries per chunk ------------------------------------------------------
 // info[c] = (position + 1 of the last head in chunk c, 0 if none) << 32 | heads in chunk c
 __global__ void __launch_bounds__(256)
-sw_chunk_heads(const uint64_t *__restrict__ sorted, int n, int idx_bits, int n_chunks, uint64_t *__restrict__ info) {
+sw_chunk_heads(const uint64_t *__restrict__ w0, const uint64_t *__restrict__ w1, int plan_slot, uint64_t *__restrict__ info) {
+    const SweepPlan &plan = c_sweep_plan[plan_slot];
+    const uint64_t *__restrict__ sorted = (plan.passes & 1) ? w1 : w0;     // where the last pass left the words
+    const int n = plan.m, idx_bits = plan.g.idx_bits, n_chunks = plan.n_chunks;
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n_chunks) return;
@@ -560,9 +625,11 @@ sw_chunk_heads(const uint64_t *__restrict__ sorted, int n, int idx_bits, int n_c
 // single block: chunk_off = exclusive sum of the head counts, ownerpos = exclusive max of lastpos.
 // Batches of 4096 chunks, coalesced 32-byte loads per thread, the next batch in flight during the scan.
 __global__ void __launch_bounds__(1024)
-sw_chunk_scan(const uint64_t *__restrict__ info, int n_chunks, uint32_t *__restrict__ chunk_off,
+sw_chunk_scan(const uint64_t *__restrict__ info, int plan_slot, uint32_t *__restrict__ chunk_off,
               uint32_t *__restrict__ ownerpos, int32_t *__restrict__ nv_out) {
     constexpr int IPT = 4;
+    const int n_chunks = c_sweep_plan[plan_slot].n_chunks;
+    if (n_chunks == 0) return;
     __shared__ uint32_t ssum[33], smax[33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t csum = 0, cmax = 0;     // carried over the batches (block-uniform)
@@ -666,9 +733,13 @@ __device__ __forceinline__ void sw_emit(int16_t *__restrict__ out, uint32_t vid,
 // per step instead of 7.
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
-sw_reduce(const uint64_t *__restrict__ sorted, int n, const uint64_t *__restrict__ pay, SweepGeom g, int n_chunks,
+sw_reduce(const uint64_t *__restrict__ w0, const uint64_t *__restrict__ w1, const uint64_t *__restrict__ pay, int plan_slot,
           const uint32_t *__restrict__ chunk_off, const uint32_t *__restrict__ ownerpos,
           uint32_t *__restrict__ slots, uint64_t *__restrict__ slotkey, int16_t *__restrict__ out) {
+    const SweepPlan &plan = c_sweep_plan[plan_slot];
+    const SweepGeom &g = plan.g;
+    const uint64_t *__restrict__ sorted = (plan.passes & 1) ? w1 : w0;
+    const int n = plan.m, n_chunks = plan.n_chunks;
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n_chunks) return;
@@ -821,14 +892,25 @@ sw_reduce(const uint64_t *__restrict__ sorted, int n, const uint64_t *__restrict
 // ---- 6. the voxels that span chunks -----------------------------------------------------
 __global__ void __launch_bounds__(256)
 sw_finalize_open(const uint64_t *__restrict__ info, const uint32_t *__restrict__ chunk_off,
-                 const uint32_t *__restrict__ slots, const uint64_t *__restrict__ slotkey, int n_chunks,
-                 SweepGeom g, int16_t *__restrict__ out) {
+                 const uint32_t *__restrict__ slots, const uint64_t *__restrict__ slotkey, int plan_slot,
+                 int16_t *__restrict__ out) {
+    const SweepPlan &plan = c_sweep_plan[plan_slot];
+    const SweepGeom &g = plan.g;
+    const int n_chunks = plan.n_chunks;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chunks || slots[8 * (size_t)c + 7] == 0) return;
     uint32_t a[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) a[k] = slots[8 * (size_t)c + k];
     sw_emit(out, chunk_off[c] + (uint32_t)info[c] - 1u, a, slotkey[c], g);
+}
+
+// the result word: a negative status beats the count (a look-back that gave up, inconsistent counts)
+__global__ void sw_result(int32_t *__restrict__ nv, const uint32_t *__restrict__ err, int plan_slot) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const SweepPlan &plan = c_sweep_plan[plan_slot];
+    if (plan.status != 0 || plan.m == 0) return;                 // sw_plan wrote the result already
+    if (*err != 0 || *nv < 1 || *nv > plan.m) *nv = -2;
 }
 
 // ---- host side ----------------------------------------------------------------------------
@@ -911,13 +993,14 @@ inline int voxel_slab_plan(VoxelScratch &s, const int16_t *rec, int n, int leaf,
     return 0;
 }
 
-// Returns the voxel count (>= 0), -2 on a CUDA error, -3 on allocation failure, -4 when the sort
-// word does not fit (the caller picks the pair sort then).  Two host synchronisations: the occupied
-// box has to reach the host before the key layout is fixed, and the count at the end.
+// Enqueues the whole merge on `cs` without any host synchronisation.  *nv_dev_out (device int32) receives the
+// voxel count when the stream gets there, or -4 when the sort word does not fit (the caller picks another
+// variant), or -2 (a look-back gave up / inconsistent counts).  Returns 0, -2 on a CUDA error, -3 on allocation
+// failure, -4 when the limits are known to be exceeded up front.
 // slab: merge only the points with kz_lo <= floor(z / leaf) < kz_hi.
 template <int BITS, int THREADS, int ITEMS>
-inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int leaf, int16_t *out, cudaStream_t cs,
-                             int sm_count, bool slab = false, int kz_lo = 0, int kz_hi = 0) {
+inline int voxel_merge_sweep_enqueue(VoxelScratch &s, const int16_t *rec, int n, int leaf, int16_t *out, cudaStream_t cs,
+                                     int sm_count, int plan_slot, bool slab, int kz_lo, int kz_hi, int32_t **nv_dev_out) {
     using Cfg = SweepPassCfg<BITS, THREADS, ITEMS>;
     constexpr int BINS = Cfg::BINS;
     SweepGeom g = sweep_base_geom(leaf);
@@ -926,72 +1009,55 @@ inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int lea
     if (slab) {
         g.z_lo = std::max(0, std::min(zbins, kz_lo + g.K));
         g.z_hi = std::max(0, std::min(zbins, kz_hi + g.K));
-        if (g.z_lo >= g.z_hi) return 0;
     }
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    // sized for the worst case (every point inside, full-range keys) so that nothing is allocated
-    // between the two phases:
-    // [bounds][words0][words1][pay] | zeroed: [ghist][tickets][err][slot counter][group
-    // words][status][slots] |
-    // [info][chunk_off][ownerpos][slotkey][nv]
+    // sized for the worst case (every point inside, full-range keys): the plan only exists on the device
+    // [bounds][plan][nv, err][words0][words1][pay] | zeroed: [ghist][tickets][slot counter][group words][status][slots] |
+    // [info][chunk_off][ownerpos][slotkey]
     const int passes_max = (3 * sweep_bits_for(zbins) + BITS - 1) / BITS;
     const int tiles_max = (n + Cfg::TILE - 1) / Cfg::TILE, chunks_max = (n + SW_CHUNK - 1) / SW_CHUNK;
     const int groups_max = (tiles_max + SW_GROUP - 1) / SW_GROUP;
-    const size_t o_bounds = 0, o_w0 = al(64), o_w1 = o_w0 + al((size_t)n * 8), o_pay = o_w1 + al((size_t)n * 8),
+    const size_t o_bounds = 0, o_plan = al(64), o_nv = o_plan + al(sizeof(SweepPlan)), o_w0 = o_nv + al(64),
+                 o_w1 = o_w0 + al((size_t)n * 8), o_pay = o_w1 + al((size_t)n * 8),
                  o_zero = o_pay + al((size_t)n * 8),
-                 o_ghist = o_zero, o_ticket = o_ghist + al((size_t)passes_max * BINS * 4), o_err = o_ticket + al(64),
-                 o_cnt = o_err + al(64), o_gstat = o_cnt + al(64),
+                 o_ghist = o_zero, o_ticket = o_ghist + al((size_t)passes_max * BINS * 4), o_cnt = o_ticket + al(64),
+                 o_gstat = o_cnt + al(64),
                  o_status = o_gstat + al((size_t)passes_max * groups_max * BINS * 4),
                  o_slots = o_status + al((size_t)passes_max * tiles_max * BINS * 4),
                  o_zero_end = o_slots + al((size_t)chunks_max * 32),
                  o_info = o_zero_end, o_off = o_info + al((size_t)chunks_max * 8), o_owner = o_off + al((size_t)chunks_max * 4),
-                 o_skey = o_owner + al((size_t)chunks_max * 4), o_nv = o_skey + al((size_t)chunks_max * 8),
-                 total = o_nv + al(64);
+                 o_skey = o_owner + al((size_t)chunks_max * 4), total = o_skey + al((size_t)chunks_max * 8);
     int rc = sweep_reserve(s, total);
     if (rc) return rc;
-    // ---- phase 0: occupied box (and the slab's population)
     uint32_t *bounds = (uint32_t *)(s.buf + o_bounds);
-    if (cudaMemsetAsync(bounds, 0, 64, cs) != cudaSuccess || cudaMemsetAsync(bounds, 0xFF, 12, cs) != cudaSuccess) return -2;
+    SweepPlan *d_plan = (SweepPlan *)(s.buf + o_plan);
+    int32_t *nv_dev = (int32_t *)(s.buf + o_nv);
+    uint32_t *err = (uint32_t *)(s.buf + o_nv) + 1;
+    *nv_dev_out = nv_dev;
+    if (cudaMemsetAsync(bounds, 0, o_w0, cs) != cudaSuccess || cudaMemsetAsync(bounds, 0xFF, 12, cs) != cudaSuccess ||
+        cudaMemsetAsync(s.buf + o_zero, 0, o_zero_end - o_zero, cs) != cudaSuccess)
+        return -2;
+    if (slab && g.z_lo >= g.z_hi) return 0;        // empty slab: *nv_dev is 0
+    // ---- occupied box (and the slab's population), then the plan, on the device
     const int kh_tiles = (n + SW_KH_TILE - 1) / SW_KH_TILE;
     const int kh_grid = std::min(kh_tiles, std::max(1, sm_count) * 8);
     sw_bounds<false><<<kh_grid, SW_KH_THREADS, 0, cs>>>(rec, n, g, bounds, nullptr, 0, 0);
-    uint32_t *hb = (uint32_t *)s.h_count;
-    if (cudaMemcpyAsync(hb, bounds, 28, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return -2;
-    if (cudaStreamSynchronize(cs) != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
-    const int m = (int)hb[6];         // points to sort
-    if (m == 0) return 0;
-    if (m > n) return -2;
-    g.x0 = (int)hb[0]; g.y0 = (int)hb[1]; g.z0 = (int)hb[2];
-    g.dx = hb[3] - hb[0] + 1;
-    g.dy = hb[4] - hb[1] + 1;
-    g.mdx = g.dx > 1 ? ~0ull / g.dx + 1ull : 0ull;
-    g.mdy = g.dy > 1 ? ~0ull / g.dy + 1ull : 0ull;
-    const long long dz = (long long)hb[5] - hb[2] + 1;
-    g.idx_bits = sweep_bits_for(slab ? m : n);
-    const int key_bits = sweep_bits_for((long long)g.dx * g.dy * dz);     // <= 6554^3 < 2^39 at leaf 10; < 2^48 always
-    if (key_bits + g.idx_bits > 64) return -4;
-    // the multiply-high divisions in sw_emit are exact while key * d stays below 2^64
-    if ((double)g.dx * g.dy * (double)dz * (double)std::max(g.dx, g.dy) >= 9.0e18) return -4;
-    const int passes = (key_bits + BITS - 1) / BITS;
-    const int n_tiles = (m + Cfg::TILE - 1) / Cfg::TILE;
-    const int n_chunks = (m + SW_CHUNK - 1) / SW_CHUNK;
+    sw_plan<<<1, 32, 0, cs>>>(bounds, g, n, slab ? 1 : 0, Cfg::TILE, BITS, d_plan, nv_dev);
+    if (cudaMemcpyToSymbolAsync(c_sweep_plan, d_plan, sizeof(SweepPlan), (size_t)plan_slot * sizeof(SweepPlan),
+                                cudaMemcpyDeviceToDevice, cs) != cudaSuccess)
+        return -2;
     uint64_t *w0 = (uint64_t *)(s.buf + o_w0), *w1 = (uint64_t *)(s.buf + o_w1), *pay = (uint64_t *)(s.buf + o_pay);
     uint32_t *ghist = (uint32_t *)(s.buf + o_ghist), *ticket = (uint32_t *)(s.buf + o_ticket),
-             *err = (uint32_t *)(s.buf + o_err), *slot_counter = (uint32_t *)(s.buf + o_cnt),
+             *slot_counter = (uint32_t *)(s.buf + o_cnt),
              *status = (uint32_t *)(s.buf + o_status), *slots = (uint32_t *)(s.buf + o_slots),
              *gstatus = (uint32_t *)(s.buf + o_gstat),
              *chunk_off = (uint32_t *)(s.buf + o_off), *ownerpos = (uint32_t *)(s.buf + o_owner);
     uint64_t *info = (uint64_t *)(s.buf + o_info), *slotkey = (uint64_t *)(s.buf + o_skey);
-    int32_t *nv_dev = (int32_t *)(s.buf + o_nv);
-    // only what this run touches is cleared: [ghist .. status of `passes` x `n_tiles`] and the slots
-    if (cudaMemsetAsync(s.buf + o_zero, 0, (o_status - o_zero) + al((size_t)passes * n_tiles * BINS * 4), cs) != cudaSuccess ||
-        cudaMemsetAsync(slots, 0, (size_t)n_chunks * 32, cs) != cudaSuccess)
-        return -2;
     if (slab)
-        sw_keys_hist<BITS, true><<<kh_grid, SW_KH_THREADS, (size_t)passes * BINS * 4, cs>>>(rec, n, g, passes, w0, pay, ghist, slot_counter);
+        sw_keys_hist<BITS, true><<<kh_grid, SW_KH_THREADS, (size_t)passes_max * BINS * 4, cs>>>(rec, n, plan_slot, w0, pay, ghist, slot_counter);
     else
-        sw_keys_hist<BITS, false><<<kh_grid, SW_KH_THREADS, (size_t)passes * BINS * 4, cs>>>(rec, n, g, passes, w0, pay, ghist, slot_counter);
-    sw_hist_scan<BITS><<<passes, BINS, 0, cs>>>(ghist);
+        sw_keys_hist<BITS, false><<<kh_grid, SW_KH_THREADS, (size_t)passes_max * BINS * 4, cs>>>(rec, n, plan_slot, w0, pay, ghist, slot_counter);
+    sw_hist_scan<BITS><<<passes_max, BINS, 0, cs>>>(ghist);
     static const bool ballot = pipe_knob("PCS_SW_BALLOT", 1, 0, 1) != 0;     // 0: MATCH.ANY ranking (tuning knob)
 #ifdef PCS_SW_PROBES      // timing probes skip phases of sw_pass (WRONG results): only in builds made for tools/probe_vox.py
     static const int probe = pipe_knob("PCS_SW_PROBE", 0, 0, 15);
@@ -999,29 +1065,41 @@ inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int lea
     constexpr int probe = 0;
 #endif
     static const int poll_ns = pipe_knob("PCS_SW_POLL_NS", 512, 0, 4096);     // pause between look-back polls (0/64/200/600/1500 ns: 1.118/1.101/1.092/1.067/1.074 ms)
-    for (int p = 0; p < passes; ++p) {
+    for (int p = 0; p < passes_max; ++p) {
         auto kern = ballot ? sw_pass<BITS, THREADS, ITEMS, true> : sw_pass<BITS, THREADS, ITEMS, false>;
-        kern<<<n_tiles, THREADS, Cfg::SMEM, cs>>>(
-            w0, w1, m, g.idx_bits + p * BITS, ghist + (size_t)p * BINS, status + (size_t)p * n_tiles * BINS,
-            gstatus + (size_t)p * groups_max * BINS, n_tiles, ticket + p, err, probe, poll_ns);
+        kern<<<tiles_max, THREADS, Cfg::SMEM, cs>>>(
+            w0, w1, plan_slot, p, ghist + (size_t)p * BINS, status + (size_t)p * tiles_max * BINS,
+            gstatus + (size_t)p * groups_max * BINS, ticket + p, err, probe, poll_ns);
         std::swap(w0, w1);
     }
-    const int cblocks = (n_chunks + 7) / 8;
-    sw_chunk_heads<<<cblocks, 256, 0, cs>>>(w0, m, g.idx_bits, n_chunks, info);
-    sw_chunk_scan<<<1, 1024, 0, cs>>>(info, n_chunks, chunk_off, ownerpos, nv_dev);
+    // the chunk kernels pick the buffer the last pass wrote (passes is only known on the device)
+    uint64_t *wa = (uint64_t *)(s.buf + o_w0), *wb = (uint64_t *)(s.buf + o_w1);
+    const int cblocks = (chunks_max + 7) / 8;
+    sw_chunk_heads<<<cblocks, 256, 0, cs>>>(wa, wb, plan_slot, info);
+    sw_chunk_scan<<<1, 1024, 0, cs>>>(info, plan_slot, chunk_off, ownerpos, nv_dev);
     if (g.off_bits <= 5)
-        sw_reduce<true><<<cblocks, 256, 0, cs>>>(w0, m, pay, g, n_chunks, chunk_off, ownerpos, slots, slotkey, out);
+        sw_reduce<true><<<cblocks, 256, 0, cs>>>(wa, wb, pay, plan_slot, chunk_off, ownerpos, slots, slotkey, out);
     else
-        sw_reduce<false><<<cblocks, 256, 0, cs>>>(w0, m, pay, g, n_chunks, chunk_off, ownerpos, slots, slotkey, out);
-    sw_finalize_open<<<(n_chunks + 255) / 256, 256, 0, cs>>>(info, chunk_off, slots, slotkey, n_chunks, g, out);
-    if (cudaMemcpyAsync(s.h_count, nv_dev, 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return -2;
-    if (cudaMemcpyAsync(s.h_count + 1, err, 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return -2;
-    if (cudaStreamSynchronize(cs) != cudaSuccess) return -2;
+        sw_reduce<false><<<cblocks, 256, 0, cs>>>(wa, wb, pay, plan_slot, chunk_off, ownerpos, slots, slotkey, out);
+    sw_finalize_open<<<(chunks_max + 255) / 256, 256, 0, cs>>>(info, chunk_off, slots, slotkey, plan_slot, out);
+    sw_result<<<1, 32, 0, cs>>>(nv_dev, err, plan_slot);
     if (cudaGetLastError() != cudaSuccess) return -2;
-    if (s.h_count[1] != 0) return -2;           // a look-back gave up waiting
+    return 0;
+}
+
+// The synchronous form: the voxel count (>= 0), -2 on a CUDA error, -3 on allocation failure, -4 when the sort
+// word does not fit (the caller picks another variant).  One host synchronisation, at the end.
+template <int BITS, int THREADS, int ITEMS>
+inline int voxel_merge_sweep(VoxelScratch &s, const int16_t *rec, int n, int leaf, int16_t *out, cudaStream_t cs,
+                             int sm_count, int plan_slot, bool slab = false, int kz_lo = 0, int kz_hi = 0) {
+    int32_t *nv_dev = nullptr;
+    int rc = voxel_merge_sweep_enqueue<BITS, THREADS, ITEMS>(s, rec, n, leaf, out, cs, sm_count, plan_slot, slab, kz_lo, kz_hi, &nv_dev);
+    if (rc) return rc;
+    if (cudaMemcpyAsync(s.h_count, nv_dev, 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return -2;
+    if (cudaStreamSynchronize(cs) != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
     const int nv = s.h_count[0];
-    if (nv < 1 || nv > m) return -2;
-    return nv;
+    if (nv > n) return -2;
+    return nv;          // a count, or the negative status the device reported
 }
 
 }  // namespace pcs

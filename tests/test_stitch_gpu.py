@@ -406,3 +406,41 @@ def test_voxel_merge_beyond_the_uint32_sum_limit(R):
     want = R.voxel_merge(rec, 10)
     assert nv == len(want) and np.array_equal(out[: nv * 5].cpu().numpy().reshape(-1, 5), want)
     c.close()
+
+
+def test_voxel_merge_async_queue_of_frames(R):
+    """pcs_b200_voxel_merge_async_dev: several merges queued back to back on one stream, one synchronisation;
+    counts and voxels per frame against the oracle; a cloud whose sort word does not fit reports
+    PCS_ERR_UNSUPPORTED in its count."""
+    c = pcs.Context(device=0, max_streams=1)
+    rng = np.random.default_rng(41)
+    cs = torch.cuda.current_stream().cuda_stream
+    clouds, leaves = [], [10, 10, 7, 10, 1]
+    for k, n in enumerate([120000, 5, 80001, 300000, 150000]):
+        rec = random_records(rng, n)
+        span = 32768 if k == 4 else 1500 + 500 * k            # the last one: full range at leaf 1 -> the word does not fit
+        rec[:, :3] = rng.integers(-span, span, (n, 3))
+        if k == 3:
+            rec[rng.random(n) < 0.4, :3] = (9, 9, 9)
+        clouds.append(rec)
+    d_in = [torch.from_numpy(r.reshape(-1)).cuda() for r in clouds]
+    d_out = [torch.zeros(r.size, dtype=torch.int16, device="cuda") for r in clouds]
+    counts = torch.full((len(clouds),), -77, dtype=torch.int32, device="cuda")
+    for k, rec in enumerate(clouds):
+        c.voxel_merge_async_dev(d_in[k].data_ptr(), len(rec), leaves[k], d_out[k].data_ptr(), counts.data_ptr() + 4 * k, cs)
+    torch.cuda.synchronize()
+    got = counts.cpu().numpy()
+    for k, rec in enumerate(clouds[:4]):
+        want = R.voxel_merge(rec, leaves[k])
+        assert got[k] == len(want), (k, got[k], len(want))
+        assert np.array_equal(d_out[k][: got[k] * 5].cpu().numpy().reshape(-1, 5), want), k
+    assert got[4] == pcs.PCS_ERR_UNSUPPORTED
+    # a slab of cloud 0, asynchronously
+    kz = np.floor_divide(clouds[0][:, 2].astype(np.int32), 10)
+    lo, hi = int(np.percentile(kz, 30)), int(np.percentile(kz, 70))
+    c.voxel_merge_slab_async_dev(d_in[0].data_ptr(), len(clouds[0]), 10, lo, hi, d_out[0].data_ptr(), counts.data_ptr(), cs)
+    torch.cuda.synchronize()
+    want = R.voxel_merge(clouds[0][(kz >= lo) & (kz < hi)], 10)
+    nv = int(counts[0].item())
+    assert nv == len(want) and np.array_equal(d_out[0][: nv * 5].cpu().numpy().reshape(-1, 5), want)
+    c.close()
