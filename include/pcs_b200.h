@@ -283,6 +283,44 @@ PCS_API int pcs_b200_voxel_merge_slab_async_dev(pcs_ctx *ctx, const int16_t *rec
                                         int kz_lo, int kz_hi, int16_t *out_dev, int32_t *count_dev,
                                         void *cuda_stream);
 
+/* The same, for records whose number is only known on the device: n_max bounds it (grids and scratch are
+ * sized for n_max), *n_dev (device int32, <= n_max) is read by the kernels.  Used on an inbox that peer GPUs
+ * fill (pcs_b200_shard_scatter_dev). */
+PCS_API int pcs_b200_voxel_merge_counted_async_dev(pcs_ctx *ctx, const int16_t *records_dev, int n_max,
+                                           const int32_t *n_dev, int leaf_mm, int16_t *out_dev,
+                                           int32_t *count_dev, void *cuda_stream);
+
+/* Multi-GPU voxel merge, sharded BEFORE the exchange ("sharded by voxel-key range with one
+ * all-to-all"): cameras are independent up to the merge (src/pcs-multicamera-client.cpp:381-392), so every GPU
+ * keeps the records of its own cameras and only the merge's input crosses NVLink, once:
+ *   1. pcs_b200_shard_hist_dev     points per z plane of my records -> my zhist; my inbox cursor = 0
+ *      -- barrier between the ranks (the host's: symmetric-memory barrier, MPI, a socket) --
+ *   2. pcs_b200_shard_plan_dev     every rank adds all ranks' histograms (read over NVLink) and cuts the z axis
+ *                                  into n_ranks slabs of equal population: identical cuts everywhere, no collective
+ *   3. pcs_b200_shard_scatter_dev  the all-to-all: every record goes to the inbox of the rank that owns its z slab
+ *                                  (peer stores; one system-scope atomic per tile and destination reserves the run)
+ *      -- barrier --
+ *   4. pcs_b200_voxel_merge_counted_async_dev(inbox, capacity, cursor, ...)   each rank merges its slab
+ * Slab r of the grid ends on rank r; the slabs concatenated in rank order are the single-GPU merge bit for bit.
+ * All pointers in pcs_shard_peers are device pointers valid on THIS rank's GPU (its own memory for `rank`,
+ * peer-mapped memory for the others: CUDA IPC via pcs_b200_ipc_open, or symmetric memory).  zhist buffers hold
+ * pcs_b200_shard_zbins(leaf_mm) uint32 each, zslab_dev as many bytes, kz_splits_dev n_ranks + 1 int32. */
+typedef struct pcs_shard_peers {
+    int32_t n_ranks, rank;                 /* n_ranks <= 8 */
+    void *inbox_dev[8];                    /* capacity_records x 10 bytes each, 16-byte aligned */
+    uint32_t *cursor_dev[8];               /* records received so far (the inbox's fill count) */
+    const uint32_t *zhist_dev[8];
+    int64_t capacity_records;
+} pcs_shard_peers;
+PCS_API int pcs_b200_shard_zbins(int leaf_mm);
+PCS_API int pcs_b200_shard_hist_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, uint32_t *zhist_dev,
+                            uint32_t *cursor_dev, void *cuda_stream);
+PCS_API int pcs_b200_shard_plan_dev(pcs_ctx *ctx, const pcs_shard_peers *peers, int leaf_mm, int32_t *kz_splits_dev,
+                            uint8_t *zslab_dev, void *cuda_stream);
+PCS_API int pcs_b200_shard_scatter_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm,
+                               const uint8_t *zslab_dev, const pcs_shard_peers *peers, uint32_t *err_dev,
+                               void *cuda_stream);
+
 /* Sharded voxel merge (multi-GPU: SURVEY s8(e) "sharded by voxel-key range").  The grid is cut
  * along z into n_slabs slabs of nearly equal population: slab r holds the points with
  * kz_splits[r] <= floor(z / leaf_mm) < kz_splits[r + 1] (kz_splits: n_slabs + 1 host ints;

@@ -60,6 +60,11 @@ class IpcHandle(C.Structure):
     _fields_ = [("reserved", C.c_uint8 * 64), ("offset", C.c_uint64), ("device", C.c_uint64)]
 
 
+class ShardPeers(C.Structure):
+    _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("inbox_dev", C.c_void_p * 8), ("cursor_dev", C.c_void_p * 8),
+                ("zhist_dev", C.c_void_p * 8), ("capacity_records", C.c_int64)]
+
+
 class FrameJob(C.Structure):
     _fields_ = [("stream", C.c_int32), ("reserved", C.c_int32), ("z16_dev", C.c_void_p),
                 ("color_dev", C.c_void_p), ("payload_dev", C.c_void_p), ("xyzrgb_dev", C.c_void_p),
@@ -143,6 +148,11 @@ def _load():
         "pcs_b200_voxel_merge": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
         "pcs_b200_voxel_merge_async_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp]),
         "pcs_b200_voxel_merge_slab_async_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+        "pcs_b200_voxel_merge_counted_async_dev": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp]),
+        "pcs_b200_shard_zbins": (C.c_int, [C.c_int]),
+        "pcs_b200_shard_hist_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp]),
+        "pcs_b200_shard_plan_dev": (C.c_int, [vp, C.POINTER(ShardPeers), C.c_int, vp, vp, vp]),
+        "pcs_b200_shard_scatter_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.POINTER(ShardPeers), vp, vp]),
         "pcs_b200_voxel_slab_plan_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, i32p, i32p, vp]),
         "pcs_b200_voxel_merge_slab_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         "pcs_b200_cloud_to_ply_rows_dev": (C.c_int, [vp, vp, C.c_int, vp, vp]),
@@ -409,6 +419,22 @@ class Context:
     def voxel_merge_slab_async_dev(self, records_ptr, n, leaf_mm, kz_lo, kz_hi, out_ptr, count_ptr, cuda_stream=0):
         self._check(lib.pcs_b200_voxel_merge_slab_async_dev(self.handle, records_ptr, n, leaf_mm, kz_lo, kz_hi, out_ptr,
                                                             count_ptr, cuda_stream))
+
+    def voxel_merge_counted_async_dev(self, records_ptr, n_max, n_ptr, leaf_mm, out_ptr, count_ptr, cuda_stream=0):
+        """Merge of an inbox whose fill count is the device int32 at n_ptr (<= n_max)."""
+        self._check(lib.pcs_b200_voxel_merge_counted_async_dev(self.handle, records_ptr, n_max, n_ptr, leaf_mm, out_ptr,
+                                                               count_ptr, cuda_stream))
+
+    # ---- multi-GPU: shard by voxel-key range before the exchange
+    def shard_hist_dev(self, records_ptr, n, leaf_mm, zhist_ptr, cursor_ptr, cuda_stream=0):
+        self._check(lib.pcs_b200_shard_hist_dev(self.handle, records_ptr, n, leaf_mm, zhist_ptr, cursor_ptr, cuda_stream))
+
+    def shard_plan_dev(self, peers: "ShardPeers", leaf_mm, splits_ptr, zslab_ptr, cuda_stream=0):
+        self._check(lib.pcs_b200_shard_plan_dev(self.handle, C.byref(peers), leaf_mm, splits_ptr, zslab_ptr, cuda_stream))
+
+    def shard_scatter_dev(self, records_ptr, n, leaf_mm, zslab_ptr, peers: "ShardPeers", err_ptr, cuda_stream=0):
+        self._check(lib.pcs_b200_shard_scatter_dev(self.handle, records_ptr, n, leaf_mm, zslab_ptr, C.byref(peers), err_ptr,
+                                                   cuda_stream))
 
     def voxel_slab_plan_dev(self, records_ptr, n, leaf_mm, n_slabs, cuda_stream=0):
         """(kz_splits[n_slabs + 1], slab_points[n_slabs]): equal-population cuts of the grid along z."""

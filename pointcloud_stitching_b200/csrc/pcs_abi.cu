@@ -19,6 +19,7 @@
 #include "pcs_voxel.cuh"
 #include "pcs_voxel_sweep.cuh"
 #include "pcs_voxel_msd.cuh"
+#include "pcs_exchange.cuh"
 
 using namespace pcs;
 
@@ -1185,7 +1186,7 @@ int pcs_b200_voxel_merge_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, in
 
 // Enqueue-only forms: nothing returns to the host; *count_dev = voxel count, or a negative pcs_status.
 static int voxel_async(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, int16_t *out_dev, int32_t *count_dev,
-                       cudaStream_t cs, bool slab, int kz_lo, int kz_hi) {
+                       cudaStream_t cs, bool slab, int kz_lo, int kz_hi, const int32_t *n_dev = nullptr) {
     int rc = voxel_args_ok(ctx, records_dev, n, leaf_mm, out_dev);
     if (rc) return rc;
     if (!count_dev) return fail(ctx, PCS_ERR_INVALID, "count_dev must not be NULL");
@@ -1202,10 +1203,10 @@ static int voxel_async(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf
     int32_t *nv_dev = nullptr;
     if (ctx->voxel_variant == 3)
         rc = voxel_merge_sweep_enqueue<10, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, ctx->plan_slot,
-                                                    slab, kz_lo, kz_hi, &nv_dev);
+                                                    slab, kz_lo, kz_hi, &nv_dev, n_dev);
     else
         rc = voxel_merge_sweep_enqueue<8, 256, 16>(ctx->voxel, records_dev, n, leaf_mm, out_dev, cs, ctx->sm_count, ctx->plan_slot,
-                                                   slab, kz_lo, kz_hi, &nv_dev);
+                                                   slab, kz_lo, kz_hi, &nv_dev, n_dev);
     if (rc < 0) return voxel_fail(ctx, rc);
     CU(ctx, cudaMemcpyAsync(count_dev, nv_dev, 4, cudaMemcpyDeviceToDevice, cs));
     return PCS_OK;
@@ -1219,6 +1220,96 @@ int pcs_b200_voxel_merge_async_dev(pcs_ctx *ctx, const int16_t *records_dev, int
 int pcs_b200_voxel_merge_slab_async_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, int kz_lo, int kz_hi,
                                         int16_t *out_dev, int32_t *count_dev, void *cuda_stream) {
     return voxel_async(ctx, records_dev, n, leaf_mm, out_dev, count_dev, (cudaStream_t)cuda_stream, true, kz_lo, kz_hi);
+}
+
+int pcs_b200_voxel_merge_counted_async_dev(pcs_ctx *ctx, const int16_t *records_dev, int n_max, const int32_t *n_dev,
+                                           int leaf_mm, int16_t *out_dev, int32_t *count_dev, void *cuda_stream) {
+    if (!n_dev) return fail(ctx, PCS_ERR_INVALID, "n_dev must not be NULL");
+    return voxel_async(ctx, records_dev, n_max, leaf_mm, out_dev, count_dev, (cudaStream_t)cuda_stream, false, 0, 0, n_dev);
+}
+
+// ---- multi-GPU: shard by voxel-key range before the exchange (pcs_exchange.cuh) ---------------------------
+int pcs_b200_shard_zbins(int leaf_mm) {
+    if (leaf_mm < 1 || leaf_mm > 32767) return PCS_ERR_INVALID;
+    return sweep_zbins(sweep_base_geom(leaf_mm));
+}
+
+static int shard_peers(pcs_ctx *ctx, const pcs_shard_peers *p, XaPeers &x) {
+    if (!ctx) return fail(nullptr, PCS_ERR_INVALID, "null context");
+    if (!p || p->n_ranks < 1 || p->n_ranks > XA_MAX_RANKS || p->rank < 0 || p->rank >= p->n_ranks || p->capacity_records < 1)
+        return fail(ctx, PCS_ERR_INVALID, "bad peer table (1 <= n_ranks <= %d)", XA_MAX_RANKS);
+    memset(&x, 0, sizeof x);
+    x.n_ranks = p->n_ranks;
+    x.rank = p->rank;
+    x.capacity = p->capacity_records;
+    for (int r = 0; r < p->n_ranks; ++r) {
+        if (!p->inbox_dev[r] || !p->cursor_dev[r] || !p->zhist_dev[r]) return fail(ctx, PCS_ERR_INVALID, "rank %d: null pointer", r);
+        x.inbox[r] = static_cast<uint16_t *>(p->inbox_dev[r]);
+        x.cursor[r] = p->cursor_dev[r];
+        x.zhist[r] = p->zhist_dev[r];
+    }
+    return PCS_OK;
+}
+
+int pcs_b200_shard_hist_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, uint32_t *zhist_dev,
+                            uint32_t *cursor_dev, void *cuda_stream) {
+    int rc = voxel_args_ok(ctx, records_dev, n, leaf_mm, zhist_dev);
+    if (rc) return rc;
+    if (!zhist_dev || !cursor_dev) return fail(ctx, PCS_ERR_INVALID, "null buffer");
+    DeviceGuard dg_(ctx->device);
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    const SweepGeom g = sweep_base_geom(leaf_mm);
+    const int zbins = sweep_zbins(g);
+    if ((size_t)zbins * 4 > 40 * 1024) return fail(ctx, PCS_ERR_UNSUPPORTED, "leaf too small for the sharded merge (z histogram > 40 KB)");
+    CU(ctx, cudaMemsetAsync(zhist_dev, 0, (size_t)zbins * 4, cs));
+    CU(ctx, cudaMemsetAsync(cursor_dev, 0, 4, cs));       // my inbox is empty again (peers add after the barrier)
+    if (n > 0) {
+        const int tiles = (n + SW_KH_TILE - 1) / SW_KH_TILE;
+        const int grid = std::max(1, std::min(tiles, std::max(1, ctx->sm_count) * 4));
+        xa_zhist<<<grid, SW_KH_THREADS, (size_t)zbins * 4, cs>>>(records_dev, n, g, zhist_dev, zbins);
+        CU(ctx, cudaGetLastError());
+    }
+    return PCS_OK;
+}
+
+int pcs_b200_shard_plan_dev(pcs_ctx *ctx, const pcs_shard_peers *peers, int leaf_mm, int32_t *kz_splits_dev,
+                            uint8_t *zslab_dev, void *cuda_stream) {
+    XaPeers x;
+    int rc = shard_peers(ctx, peers, x);
+    if (rc) return rc;
+    if (leaf_mm < 1 || leaf_mm > 32767 || !kz_splits_dev || !zslab_dev) return fail(ctx, PCS_ERR_INVALID, "bad arguments");
+    DeviceGuard dg_(ctx->device);
+    const SweepGeom g = sweep_base_geom(leaf_mm);
+    const int zbins = sweep_zbins(g);
+    if ((size_t)zbins * 4 > 40 * 1024) return fail(ctx, PCS_ERR_UNSUPPORTED, "leaf too small for the sharded merge");
+    xa_plan<<<1, 1024, (size_t)zbins * 4, (cudaStream_t)cuda_stream>>>(x, zbins, g.K, kz_splits_dev, zslab_dev);
+    CU(ctx, cudaGetLastError());
+    return PCS_OK;
+}
+
+int pcs_b200_shard_scatter_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, const uint8_t *zslab_dev,
+                               const pcs_shard_peers *peers, uint32_t *err_dev, void *cuda_stream) {
+    XaPeers x;
+    int rc = shard_peers(ctx, peers, x);
+    if (rc) return rc;
+    if ((rc = voxel_args_ok(ctx, records_dev, n, leaf_mm, zslab_dev))) return rc;
+    if (!zslab_dev || !err_dev) return fail(ctx, PCS_ERR_INVALID, "null buffer");
+    if (n == 0) return PCS_OK;
+    DeviceGuard dg_(ctx->device);
+    const SweepGeom g = sweep_base_geom(leaf_mm);
+    const int zbins = sweep_zbins(g);
+    const size_t smem = xa_scatter_smem(zbins);
+    static bool configured = false;
+    if (!configured) {
+        CU(ctx, cudaFuncSetAttribute(xa_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured = true;
+    }
+    if (smem > 100 * 1024) return fail(ctx, PCS_ERR_UNSUPPORTED, "leaf too small for the sharded merge");
+    const int tiles = (n + XA_TILE - 1) / XA_TILE;
+    const int grid = std::max(1, std::min(tiles, std::max(1, ctx->sm_count) * 4));
+    xa_scatter<<<grid, XA_THREADS, smem, (cudaStream_t)cuda_stream>>>(records_dev, n, g, x, zslab_dev, zbins, err_dev);
+    CU(ctx, cudaGetLastError());
+    return PCS_OK;
 }
 
 int pcs_b200_voxel_slab_plan_dev(pcs_ctx *ctx, const int16_t *records_dev, int n, int leaf_mm, int n_slabs,

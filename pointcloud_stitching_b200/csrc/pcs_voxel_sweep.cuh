@@ -113,8 +113,9 @@ __device__ __forceinline__ int sw_half(const uint32_t (&w)[20], int h) {   // ha
 template <bool HIST>
 __global__ void __launch_bounds__(SW_KH_THREADS)
 sw_bounds(const int16_t *__restrict__ rec, int n, SweepGeom g, uint32_t *__restrict__ bounds,
-          uint32_t *__restrict__ zhist, int zbins, int zhist_in_smem) {
+          uint32_t *__restrict__ zhist, int zbins, int zhist_in_smem, const int32_t *__restrict__ n_dev = nullptr) {
     extern __shared__ uint32_t sw_zh[];
+    if (n_dev) n = max(0, min(n, *n_dev));       // the point count lives on the device (an inbox filled by peers)
     __shared__ uint32_t red[7];
     if (threadIdx.x < 7) red[threadIdx.x] = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
     uint32_t *zh = (HIST && zhist_in_smem) ? sw_zh : zhist;
@@ -230,8 +231,9 @@ template <int BITS, bool FILTER>
 __global__ void __launch_bounds__(SW_KH_THREADS)
 sw_keys_hist(const int16_t *__restrict__ rec, int n, int plan_slot,
              uint64_t *__restrict__ words, uint64_t *__restrict__ pay, uint32_t *__restrict__ ghist,
-             uint32_t *__restrict__ slot_counter) {
+             uint32_t *__restrict__ slot_counter, const int32_t *__restrict__ n_dev = nullptr) {
     constexpr int BINS = 1 << BITS;
+    if (n_dev) n = max(0, min(n, *n_dev));
     const SweepPlan &plan = c_sweep_plan[plan_slot];
     const SweepGeom &g = plan.g;
     const int passes = plan.passes;
@@ -1000,7 +1002,8 @@ inline int voxel_slab_plan(VoxelScratch &s, const int16_t *rec, int n, int leaf,
 // slab: merge only the points with kz_lo <= floor(z / leaf) < kz_hi.
 template <int BITS, int THREADS, int ITEMS>
 inline int voxel_merge_sweep_enqueue(VoxelScratch &s, const int16_t *rec, int n, int leaf, int16_t *out, cudaStream_t cs,
-                                     int sm_count, int plan_slot, bool slab, int kz_lo, int kz_hi, int32_t **nv_dev_out) {
+                                     int sm_count, int plan_slot, bool slab, int kz_lo, int kz_hi, int32_t **nv_dev_out,
+                                     const int32_t *n_dev = nullptr) {
     using Cfg = SweepPassCfg<BITS, THREADS, ITEMS>;
     constexpr int BINS = Cfg::BINS;
     SweepGeom g = sweep_base_geom(leaf);
@@ -1041,8 +1044,9 @@ inline int voxel_merge_sweep_enqueue(VoxelScratch &s, const int16_t *rec, int n,
     // ---- occupied box (and the slab's population), then the plan, on the device
     const int kh_tiles = (n + SW_KH_TILE - 1) / SW_KH_TILE;
     const int kh_grid = std::min(kh_tiles, std::max(1, sm_count) * 8);
-    sw_bounds<false><<<kh_grid, SW_KH_THREADS, 0, cs>>>(rec, n, g, bounds, nullptr, 0, 0);
-    sw_plan<<<1, 32, 0, cs>>>(bounds, g, n, slab ? 1 : 0, Cfg::TILE, BITS, d_plan, nv_dev);
+    sw_bounds<false><<<kh_grid, SW_KH_THREADS, 0, cs>>>(rec, n, g, bounds, nullptr, 0, 0, n_dev);
+    // (with a device-side count the slots are the record indices below that count: index bits from m, as for a slab)
+    sw_plan<<<1, 32, 0, cs>>>(bounds, g, n, (slab || n_dev) ? 1 : 0, Cfg::TILE, BITS, d_plan, nv_dev);
     if (cudaMemcpyToSymbolAsync(c_sweep_plan, d_plan, sizeof(SweepPlan), (size_t)plan_slot * sizeof(SweepPlan),
                                 cudaMemcpyDeviceToDevice, cs) != cudaSuccess)
         return -2;
@@ -1054,9 +1058,9 @@ inline int voxel_merge_sweep_enqueue(VoxelScratch &s, const int16_t *rec, int n,
              *chunk_off = (uint32_t *)(s.buf + o_off), *ownerpos = (uint32_t *)(s.buf + o_owner);
     uint64_t *info = (uint64_t *)(s.buf + o_info), *slotkey = (uint64_t *)(s.buf + o_skey);
     if (slab)
-        sw_keys_hist<BITS, true><<<kh_grid, SW_KH_THREADS, (size_t)passes_max * BINS * 4, cs>>>(rec, n, plan_slot, w0, pay, ghist, slot_counter);
+        sw_keys_hist<BITS, true><<<kh_grid, SW_KH_THREADS, (size_t)passes_max * BINS * 4, cs>>>(rec, n, plan_slot, w0, pay, ghist, slot_counter, n_dev);
     else
-        sw_keys_hist<BITS, false><<<kh_grid, SW_KH_THREADS, (size_t)passes_max * BINS * 4, cs>>>(rec, n, plan_slot, w0, pay, ghist, slot_counter);
+        sw_keys_hist<BITS, false><<<kh_grid, SW_KH_THREADS, (size_t)passes_max * BINS * 4, cs>>>(rec, n, plan_slot, w0, pay, ghist, slot_counter, n_dev);
     sw_hist_scan<BITS><<<passes_max, BINS, 0, cs>>>(ghist);
     static const bool ballot = pipe_knob("PCS_SW_BALLOT", 1, 0, 1) != 0;     // 0: MATCH.ANY ranking (tuning knob)
 #ifdef PCS_SW_PROBES      // timing probes skip phases of sw_pass (WRONG results): only in builds made for tools/probe_vox.py

@@ -222,6 +222,77 @@ class SymmetricFrameSet:
         self.handle.barrier()
 
 
+class ShardedMerge:
+    """Voxel merge of a multi-camera cloud that is NEVER assembled: sharded by voxel-key range before the exchange
+    (SURVEY s8(e)).  Every rank holds only its own cameras' records; per frame
+
+        hist (my points per z plane) -> barrier -> plan (all ranks derive the same equal-population z cuts from
+        everybody's histogram, read over NVLink) -> scatter (all-to-all: each record goes to the inbox of the rank
+        that owns its slab, peer stores from the binning kernel) -> barrier -> merge of my inbox
+
+    and slab r of the merged grid stays on rank r (``out``, ``count``).  The slabs concatenated in rank order are the
+    single-GPU merge of all cameras, bit for bit.  The exchange buffers (histogram, inbox cursor, inbox) live in
+    one symmetric-memory allocation per frame slot; torch symmetric memory is used for the allocation, the
+    rendezvous and the device-side barrier only.  Nothing in a frame returns to the host.
+    """
+
+    def __init__(self, ctx, rank, world, device, n_total, leaf_mm, n_slots=1, group=None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm
+
+        import pointcloud_stitching_b200 as pcs
+        self.ctx, self.rank, self.world, self.leaf = ctx, rank, world, leaf_mm
+        self.capacity = int(n_total)               # worst case: every point of the cloud falls into one slab
+        self.zbins = pcs.lib.pcs_b200_shard_zbins(leaf_mm)
+        if self.zbins < 0:
+            raise ValueError("bad leaf")
+        al = lambda b: (b + 255) & ~255            # noqa: E731
+        self.o_cursor, self.o_zhist = 0, 256
+        self.o_inbox = self.o_zhist + al(self.zbins * 4)
+        self.slot_bytes = self.o_inbox + al(self.capacity * RECORD_BYTES)
+        self.n_slots = n_slots
+        self.raw = symm.empty(self.slot_bytes * n_slots, dtype=torch.uint8, device=device)
+        self.raw.zero_()
+        self.handle = symm.rendezvous(self.raw, group if group is not None else dist.group.WORLD)
+        bases = list(self.handle.buffer_ptrs)
+        assert bases[rank] == self.raw.data_ptr()
+        self.peers = []
+        for k in range(n_slots):
+            p = pcs.ShardPeers()
+            p.n_ranks, p.rank, p.capacity_records = world, rank, self.capacity
+            for r in range(world):
+                b = bases[r] + k * self.slot_bytes
+                p.cursor_dev[r], p.zhist_dev[r], p.inbox_dev[r] = b + self.o_cursor, b + self.o_zhist, b + self.o_inbox
+            self.peers.append(p)
+        # local, per slot: the cuts, the plane -> rank table, the error flag, the voxel count
+        self.splits = torch.zeros(n_slots, world + 1, dtype=torch.int32, device=device)
+        self.zslab = torch.zeros(n_slots, (self.zbins + 15) & ~15, dtype=torch.uint8, device=device)
+        self.err = torch.zeros(n_slots, dtype=torch.int32, device=device)
+        self.count = torch.zeros(n_slots, dtype=torch.int32, device=device)
+
+    def local_ptrs(self, slot):
+        base = self.raw.data_ptr() + slot * self.slot_bytes
+        return base + self.o_cursor, base + self.o_zhist, base + self.o_inbox
+
+    def barrier(self):
+        self.handle.barrier()
+
+    def run(self, slot, records_ptr, n_own, out, cuda_stream=0):
+        """Enqueue one frame on the CURRENT torch stream (``cuda_stream`` is its raw handle): ``out`` (int16, capacity
+        ``capacity * 5``) receives this rank's slab, ``self.count[slot]`` its voxel count, ``self.splits[slot]`` the cuts."""
+        cursor, zhist, inbox = self.local_ptrs(slot)
+        p = self.peers[slot]
+        self.ctx.shard_hist_dev(records_ptr, n_own, self.leaf, zhist, cursor, cuda_stream)
+        self.handle.barrier()
+        self.ctx.shard_plan_dev(p, self.leaf, self.splits[slot].data_ptr(), self.zslab[slot].data_ptr(), cuda_stream)
+        self.ctx.shard_scatter_dev(records_ptr, n_own, self.leaf, self.zslab[slot].data_ptr(), p, self.err[slot].data_ptr(),
+                                   cuda_stream)
+        self.handle.barrier()
+        self.ctx.voxel_merge_counted_async_dev(inbox, self.capacity, cursor, self.leaf, out.data_ptr(),
+                                               self.count[slot].data_ptr(), cuda_stream)
+
+
 def sharded_voxel_merge(ctx, records_ptr, n, leaf_mm, rank, world, out, cuda_stream=0, gather=True, group=None):
     """Voxel merge of a stitched cloud that every rank holds, sharded by z-slab.
 

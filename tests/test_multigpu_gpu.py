@@ -151,3 +151,68 @@ def test_single_process_pull_over_peer_access():
     for r in range(world):
         torch.cuda.synchronize(r)
         assert np.array_equal(bufs[r].wire_bytes().cpu().numpy(), want), r
+
+
+def _shard_worker(rank, world, port, cams_total, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import pointcloud_stitching_b200 as pcs
+    from pointcloud_stitching_b200 import multigpu, synth
+    dev = torch.device("cuda", rank)
+    layout = multigpu.StitchLayout([W * H] * cams_total, world)
+    mine = layout.cams_of[rank]
+    ctx = pcs.Context(device=rank, max_streams=cams_total)
+    n_frames, n_total = 3, cams_total * W * H
+    cs = torch.cuda.current_stream().cuda_stream
+    own = [torch.zeros(len(mine) * W * H * 5, dtype=torch.int16, device=dev) for _ in range(n_frames)]
+    keep, jobs = [], []
+    for i, cam in enumerate(mine):
+        ctx.set_stream(cam, pcs.stream_desc(W, H, tf=synth.TF_STITCH[cam % 8], translation=synth.D2C_BASELINE))
+        for f in range(n_frames):
+            z = torch.from_numpy(synth.depth_frame(W, H, cam, f).view(np.int16)).to(dev)
+            c = torch.from_numpy(synth.color_frame(W, H, cam, f)).to(dev)
+            keep.append((z, c))
+            jobs.append((cam, z.data_ptr(), c.data_ptr(), own[f].data_ptr() + i * W * H * 10))
+    batch = ctx.batch(jobs)
+    sm = multigpu.ShardedMerge(ctx, rank, world, dev, n_total, 10, n_slots=2)
+    outs = [torch.zeros(n_total * 5, dtype=torch.int16, device=dev) for _ in range(n_frames)]
+    for rep in range(2):                 # twice: the slots (inbox, cursor, histogram) are reused
+        batch.run(cs)
+        for f in range(n_frames):
+            sm.run(f % 2, own[f].data_ptr(), len(mine) * W * H, outs[f], cs)
+            if f % 2 == 1 or f == n_frames - 1:
+                torch.cuda.synchronize()             # slot results are read before the slot is reused
+                for g in range(f - (f % 2), f + 1):
+                    nv = int(sm.count[g % 2].item())
+                    assert nv >= 0 and int(sm.err[g % 2].item()) == 0
+                    np.save(os.path.join(out_dir, "slab_r%d_f%d.npy" % (rank, g)), outs[g][: nv * 5].cpu().numpy().reshape(-1, 5))
+                    np.save(os.path.join(out_dir, "cuts_r%d_f%d.npy" % (rank, g)), sm.splits[g % 2].cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cams_total", [4, 5], ids=["equal", "ragged"])
+def test_sharded_merge_all_to_all_matches_the_single_gpu_merge(tmp_path, cams_total):
+    """Shard-before-exchange: no rank ever holds the stitched cloud; slab r of the merged grid ends on rank r and the
+    slabs in rank order are the oracle's merge of ALL cameras, bit for bit; every rank derives the same cuts."""
+    import oracle
+    from pointcloud_stitching_b200 import synth
+    world = 2
+    mp.spawn(_shard_worker, args=(world, _free_port(), cams_total, str(tmp_path)), nprocs=world, join=True)
+    R = oracle.restatement()
+    cal = oracle.make_calib(W, H, translation=synth.D2C_BASELINE)
+    for f in range(3):
+        rec = np.concatenate([R.frame(cal, synth.depth_frame(W, H, cam, f), synth.color_frame(W, H, cam, f), 3, W * 3,
+                                      synth.TF_STITCH[cam % 8]) for cam in range(cams_total)])
+        want = R.voxel_merge(rec, 10)
+        slabs = [np.load(os.path.join(str(tmp_path), "slab_r%d_f%d.npy" % (r, f))) for r in range(world)]
+        cuts = [np.load(os.path.join(str(tmp_path), "cuts_r%d_f%d.npy" % (r, f))) for r in range(world)]
+        assert np.array_equal(cuts[0], cuts[1])
+        assert np.array_equal(np.concatenate(slabs), want), f
+        kz = np.floor_divide(rec[:, 2].astype(np.int32), 10)
+        assert cuts[0][0] == kz.min() and cuts[0][-1] == kz.max() + 1
+        pts = [int(((kz >= cuts[0][r]) & (kz < cuts[0][r + 1])).sum()) for r in range(world)]
+        assert max(pts) < 0.6 * len(rec)              # equal-population cuts (whole planes)
+        assert all(len(s) > 0 for s in slabs)
