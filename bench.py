@@ -320,7 +320,7 @@ def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, worl
         if world > 1:
             return None      # a single-GPU configuration
     else:
-        cams, w, h, frames = 20, 848, 480, 4
+        cams, w, h, frames = 20, 848, 480, 8
     npts = w * h
     dev = torch.device("cuda", local)
     cs = torch.cuda.current_stream().cuda_stream
@@ -332,21 +332,35 @@ def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, worl
         d = pcs.stream_desc(w, h, tf=synth.TF_STITCH[cam % 8], translation=synth.D2C_BASELINE)
         d.color_stride = stride
         ctx.set_stream(cam, d)
-    stitched = [multigpu.StitchedBuffer(layout, rank, dev) for _ in range(frames)]
     keep = []
+    sm = None
     if world > 1:
-        fset = multigpu.SymmetricFrameSet(layout, rank, dev, w, h, frames, stride=stride)
-        for cam in layout.cams_of[rank]:
-            for f in range(frames):
+        # every rank deprojects ITS cameras only; the records are never assembled: they go straight to the rank that
+        # owns their z slab of the voxel grid (multigpu.ShardedMerge)
+        mine = layout.cams_of[rank]
+        own = [torch.zeros(max(1, len(mine)) * npts * 5, dtype=torch.int16, device=dev) for _ in range(frames)]
+        batches = []
+        for f in range(frames):
+            jobs = []
+            for i, cam in enumerate(mine):
                 col = np.zeros((h, stride), np.uint8)
                 col[:, :w * 3] = synth.color_frame(w, h, cam, f)
-                fset.upload(cam, f, synth.depth_frame(w, h, cam, f), col)
-        torch.cuda.synchronize()
-        fset.barrier()
-        pj = fset.pull_jobs(stitched)      # frame-major: [f * cams + cam]
-        batches = [ctx.batch(pj[f * cams:(f + 1) * cams]) for f in range(frames)]
+                z = torch.from_numpy(synth.depth_frame(w, h, cam, f).view(np.int16)).to(dev)
+                c = torch.from_numpy(col).to(dev)
+                keep.append((z, c))
+                jobs.append((cam, z.data_ptr(), c.data_ptr(), own[f].data_ptr() + i * npts * 10))
+            batches.append(ctx.batch(jobs) if jobs else None)
+        # `xl` exchange lanes: consecutive frames run hist / all-to-all / merge concurrently on their own streams (own
+        # merge context, own symmetric buffers and barrier pads each) -- at N = 8 a slab is ~1 M points and a lone
+        # frame is all launch and barrier latency
+        xl = max(1, min(args.merge_lanes, frames))
+        xctx = [ctx] + [pcs.Context(device=local, max_streams=1) for _ in range(xl - 1)]
+        xstreams = [torch.cuda.current_stream()] + [torch.cuda.Stream() for _ in range(xl - 1)]
+        sms = [multigpu.ShardedMerge(xctx[k], rank, world, dev, n, LEAF_MM, n_slots=(frames + xl - 1) // xl) for k in range(xl)]
+        sm = sms[0]
+        stitched = None
     else:
-        fset = None
+        stitched = [multigpu.StitchedBuffer(layout, rank, dev) for _ in range(frames)]
         batches = []
         for f in range(frames):
             jobs = []
@@ -364,9 +378,8 @@ def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, worl
 
     def k1_only():
         for f in range(frames):
-            batches[f].run(cs)
-        if fset is not None:
-            fset.barrier()
+            if batches[f] is not None:
+                batches[f].run(cs)
 
     # world == 1: enqueue-only merges (box, key layout, pass count and voxel count stay on the device; the counts are
     # read once, after the step's last frame) on `lanes` CUDA streams, one merge context (scratch + plan slot) each:
@@ -387,10 +400,16 @@ def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, worl
             for s2 in mstreams[1:]:
                 main.wait_stream(s2)
             return
+        # per frame: hist -> barrier -> plan -> all-to-all -> barrier -> merge of my slab; nothing returns to the host
+        main = xstreams[0]
+        for s2 in xstreams[1:]:
+            s2.wait_stream(main)
         for f in range(frames):
-            total, mine = multigpu.sharded_voxel_merge(ctx, stitched[f].payload.data_ptr(), n, LEAF_MM, rank, world,
-                                                       outs[f], cs, gather=False)
-            nv[f] = mine
+            k = f % xl
+            with torch.cuda.stream(xstreams[k]):
+                sms[k].run(f // xl, own[f].data_ptr(), len(layout.cams_of[rank]) * npts, outs[f], xstreams[k].cuda_stream)
+        for s2 in xstreams[1:]:
+            main.wait_stream(s2)
 
     def step():
         k1_only()
@@ -402,8 +421,12 @@ def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, worl
     ms_merge = timer.run(merge_only, iters)
     if world == 1:
         nv = [int(v) for v in counts.cpu().tolist()]
-        if min(nv) < 0:
-            raise RuntimeError("voxel merge reported status %d" % min(nv))
+    else:
+        nv = [int(sms[f % xl].count[f // xl].item()) for f in range(frames)]
+        if any(int(x.err.abs().sum().item()) != 0 for x in sms):
+            raise RuntimeError("an inbox overflowed")
+    if min(nv) < 0:
+        raise RuntimeError("voxel merge reported status %d" % min(nv))
     # voxels over all ranks (each rank keeps its z-slab of the grid)
     nv_local = torch.tensor([float(sum(nv))], device=dev, dtype=torch.float64)
     if world > 1:
@@ -413,12 +436,15 @@ def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, worl
     # roofline of the merge, SURVEY s8(d): lower bound 10 B/pt read + 10 B/voxel written
     alg = 10.0 * pts_step / world + 10.0 * sum(nv)
     achieved = alg / (ms_merge * 1e-3) / 1e9
-    res = {"workload": "%d cams x %dx%d, %d stitched frames per step, K1 -> in-place concat -> voxel-grid merge %d mm%s" % (
-               cams, w, h, frames, LEAF_MM, "" if world == 1 else " (pull exchange; merge sharded by z-slab, slabs stay on their GPUs)"),
+    res = {"workload": "%d cams x %dx%d, %d stitched frames per step, K1 -> %s -> voxel-grid merge %d mm" % (
+               cams, w, h, frames, "in-place concat" if world == 1 else
+               "records sharded by z slab of the voxel grid BEFORE the exchange (per-rank z histogram, identical cuts on every "
+               "GPU, all-to-all as peer stores over NVLink: 10 B/pt x (N-1)/N, each record crosses once); slab r stays on GPU r",
+               LEAF_MM),
            "n_gpus": world, "points_per_step": pts_step, "voxels_per_step": nv_total,
            "value": pts_step / (ms_step * 1e-3) / 1e6, "unit": "Mpoints/s", "ms_per_step": ms_step,
            "k1_ms_per_step": ms_k1, "merge_ms_per_step": ms_merge, "merge_ms_per_frame": ms_merge / frames,
-           "merge_lanes": lanes,
+           "merge_lanes": lanes if world == 1 else xl,
            "gpu_launches_per_step": None,
            "roofline": {"bound": "hbm", "kernel": "voxel merge (sw_keys_hist + sw_pass x P + sw_reduce; sw_pass dominant)",
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -432,20 +458,24 @@ def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, worl
         recs = []
         for cam in range(cams):
             recs.append(oracle_records("baseline", cam, synth.depth_frame(w, h, cam, 0), synth.color_frame(w, h, cam, 0), w, h))
-        got_st = stitched[0].payload.cpu().numpy().view(np.int16).reshape(-1, 5)
-        ok = np.array_equal(got_st, np.concatenate(recs))
         t0 = time.perf_counter()
         want_vox = R.voxel_merge(np.concatenate(recs), LEAF_MM)
         t_vox = time.perf_counter() - t0
         if world == 1:
+            got_st = stitched[0].payload.cpu().numpy().view(np.int16).reshape(-1, 5)
+            ok = np.array_equal(got_st, np.concatenate(recs))
             got = outs[0][: nv[0] * 5].cpu().numpy().reshape(-1, 5)
             ok = ok and nv[0] == len(want_vox) and np.array_equal(got, want_vox)
         else:
-            splits, _ = ctx.voxel_slab_plan_dev(stitched[0].payload.data_ptr(), n, LEAF_MM, world, cs)
+            # this rank's slab of the oracle's merge of ALL cameras, cut where the GPUs cut
+            splits = sm.splits[0].cpu().numpy()
             kz = np.floor_divide(want_vox[:, 2].astype(np.int32), LEAF_MM)
             sel = want_vox[(kz >= splits[rank]) & (kz < splits[rank + 1])]
             got = outs[0][: nv[0] * 5].cpu().numpy().reshape(-1, 5)
-            ok = ok and nv[0] == len(sel) and np.array_equal(got, sel)
+            ok = nv[0] == len(sel) and np.array_equal(got, sel)
+            allcuts = [torch.zeros_like(sm.splits[0]) for _ in range(world)]
+            dist.all_gather(allcuts, sm.splits[0].contiguous())
+            ok = ok and all(bool(torch.equal(c, allcuts[0])) for c in allcuts)
         flag = torch.tensor([1.0 if ok else 0.0], device=dev)
         if world > 1:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -463,9 +493,13 @@ def bench_voxel_config(name, torch, dist, pcs, synth, multigpu, args, rank, worl
                                              "(qsort, own spec) %.1f ms" % (n, t_cat * 1e3, t_vox * 1e3)}
     res["check"] = check
     for b in batches:
-        b.close()
+        if b is not None:
+            b.close()
     for c in mctx[1:]:
         c.close()
+    if world > 1:
+        for c in xctx[1:]:
+            c.close()
     ctx.close()
     return res
 
