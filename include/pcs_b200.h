@@ -92,9 +92,10 @@ typedef struct pcs_config {
 } pcs_config;
 
 /* One frame of work for the batched device-resident path. */
+#define PCS_B200_JOB_REMOTE_FRAME 1   /* flags: z16_dev / color_dev point into a peer GPU's memory (pull exchange) */
 typedef struct pcs_frame_job {
     int32_t stream;            /* index given to pcs_b200_set_stream */
-    int32_t reserved;
+    int32_t reserved;          /* flags (0, or PCS_B200_JOB_REMOTE_FRAME: a scheduling hint, results do not depend on it) */
     const uint16_t *z16_dev;   /* depth.height * depth.width */
     const uint8_t *color_dev;  /* color.height * color_stride bytes */
     int16_t *payload_dev;      /* depth.width*depth.height records (10 B each) */

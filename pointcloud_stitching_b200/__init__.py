@@ -291,12 +291,12 @@ class Context:
     def _job_array(jobs):
         arr = (FrameJob * len(jobs))()
         for i, j in enumerate(jobs):
-            j = tuple(j) + (None,) * (6 - len(j))
-            arr[i] = FrameJob(j[0], 0, j[1], j[2], j[3], j[4], j[5])
+            j = tuple(j) + (None,) * (7 - len(j))
+            arr[i] = FrameJob(j[0], int(j[6] or 0), j[1], j[2], j[3], j[4], j[5])
         return arr
 
     def batch(self, jobs):
-        """jobs: iterable of (stream, z16_ptr, color_ptr, payload_ptr[, xyzrgb_ptr[, count_ptr]])."""
+        """jobs: iterable of (stream, z16_ptr, color_ptr, payload_ptr[, xyzrgb_ptr[, count_ptr[, flags]]])."""
         h = C.c_void_p()
         self._check(lib.pcs_b200_batch_create(self.handle, self._job_array(jobs), len(jobs), C.byref(h)))
         return Batch(self, h)

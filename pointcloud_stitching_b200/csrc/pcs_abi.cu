@@ -690,7 +690,9 @@ static int batch_create_impl(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs
         if (ok) {
             std::vector<StreamParams> sp(ctx->max_streams);
             for (int i = 0; i < ctx->max_streams; ++i) sp[i] = ctx->streams[i].params;
-            int rc = pipe_build(b->pipe, b->jobs, sp, ctx->sm_count, n_peers, peer_delta);
+            bool remote = false;
+            for (int j = 0; j < n_jobs; ++j) remote = remote || (jobs[j].reserved & PCS_B200_JOB_REMOTE_FRAME) != 0;
+            int rc = pipe_build(b->pipe, b->jobs, sp, ctx->sm_count, n_peers, peer_delta, remote);
             if (rc == PCS_OK) b->use_pipe = true;
             else if (ctx->kernel_variant == 2 || n_peers)
                 return bail(fail(ctx, rc, "pipelined kernel setup failed"));

@@ -214,7 +214,8 @@ class SymmetricFrameSet:
         for f in range(self.n_frames):
             for cam in range(n_cams):
                 z, c = self.ptrs(cam, f)
-                jobs.append((cam, z, c, stitched_frames[f].slot_ptr(cam)))
+                remote = 1 if self.layout.rank_of(cam) != self.rank else 0     # PCS_B200_JOB_REMOTE_FRAME
+                jobs.append((cam, z, c, stitched_frames[f].slot_ptr(cam), None, None, remote))
         return jobs
 
     def barrier(self):

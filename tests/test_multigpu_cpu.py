@@ -75,11 +75,12 @@ def test_pull_exchange_job_table():
         stitched = [multigpu.StitchedBuffer(L, rank, "cpu") for _ in range(F)]
         jobs = fs.pull_jobs(stitched)
         assert [j[0] for j in jobs] == list(range(5)) * F
-        for k, (cam, z, c, out) in enumerate(jobs):
+        for k, (cam, z, c, out, _, _, flags) in enumerate(jobs):
             f, owner = k // 5, L.rank_of(cam)
             lc = L.cams_of[owner].index(cam)
             assert z == fs.bases[owner] + depth_off(lc, f) and c == fs.bases[owner] + color_off(lc, f)
             assert out == stitched[f].slot_ptr(cam)
+            assert flags == (0 if owner == rank else 1)      # PCS_B200_JOB_REMOTE_FRAME on the peers' frames
 
 
 def _free_port():
