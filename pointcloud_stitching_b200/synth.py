@@ -62,14 +62,20 @@ def seed_for(cam: int, frame: int) -> int:
     return 0xC0FFEE ^ (cam << 16) ^ frame
 
 
+#: depth noise of the default scene (mm): a 0.8 m thick cloud per camera, ~0.84 voxels per point at the 10 mm leaf --
+#: the worst case for the voxel merge.  SMOOTH_NOISE_MM is a surface as a depth camera sees it (several points per voxel).
+NOISE_MM = 400.0
+SMOOTH_NOISE_MM = 5.0
+
+
 def depth_frame(w: int, h: int, cam: int = 0, frame: int = 0, lo: int = 300, hi: int = 6000,
-                hole_p: float = 1.0 / 16.0) -> np.ndarray:
-    """uint16[h, w]: a tilted plane plus noise clipped to [lo, hi] mm, zero with prob hole_p."""
+                hole_p: float = 1.0 / 16.0, noise_mm: float = NOISE_MM) -> np.ndarray:
+    """uint16[h, w]: a tilted plane plus noise (sigma noise_mm) clipped to [lo, hi] mm, zero with prob hole_p."""
     rng = np.random.default_rng(seed_for(cam, frame))
     yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
     base = rng.uniform(1500, 3500)
     plane = base + rng.uniform(-1.5, 1.5) * (xx - w / 2) + rng.uniform(-1.5, 1.5) * (yy - h / 2)
-    z = plane + rng.normal(0.0, 400.0, size=(h, w)).astype(np.float32)
+    z = plane + rng.normal(0.0, noise_mm, size=(h, w)).astype(np.float32)
     z = np.clip(z, lo, hi).astype(np.uint16)
     z[rng.random((h, w)) < hole_p] = 0
     return z

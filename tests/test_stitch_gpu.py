@@ -444,3 +444,63 @@ def test_voxel_merge_async_queue_of_frames(R):
     nv = int(counts[0].item())
     assert nv == len(want) and np.array_equal(d_out[0][: nv * 5].cpu().numpy().reshape(-1, 5), want)
     c.close()
+
+
+@pytest.mark.parametrize("n_ranks", [1, 3, 8])
+def test_shard_before_exchange_kernels_on_one_gpu(R, n_ranks):
+    """The all-to-all of the sharded multi-GPU merge (pcs_b200_shard_*) with every "rank" living on this GPU: each
+    rank's records are histogrammed, every rank derives the cuts from all histograms, the scatter fills the ranks'
+    inboxes, every inbox is merged with a device-side point count -- slabs in rank order == the merge of everything.
+    (tests/test_multigpu_gpu.py runs the same through NVLink on two GPUs.)"""
+    c = pcs.Context(device=0, max_streams=1)
+    rng = np.random.default_rng(50 + n_ranks)
+    leaf = 10
+    sizes = [int(rng.integers(20000, 90000)) for _ in range(n_ranks)]
+    if n_ranks > 2:
+        sizes[1] = 0                                        # a rank without points
+    recs = []
+    for k, n in enumerate(sizes):
+        r = random_records(rng, n)
+        r[:, :3] = (rng.normal(0, 700, (n, 3)) + (300 * k, 0, 150 * k)).clip(-32000, 32000).astype(np.int16)
+        if k == 0 and n:
+            r[: n // 3, :3] = (11, 12, -513)                # a crowded voxel
+        recs.append(r)
+    total = sum(sizes)
+    zbins = pcs.lib.pcs_b200_shard_zbins(leaf)
+    cs = torch.cuda.current_stream().cuda_stream
+    d_rec = [torch.from_numpy(r.reshape(-1).copy()).cuda() if len(r) else torch.zeros(8, dtype=torch.int16, device="cuda") for r in recs]
+    zh = [torch.full((zbins,), 7, dtype=torch.int32, device="cuda") for _ in range(n_ranks)]
+    cur = [torch.full((1,), 99, dtype=torch.int32, device="cuda") for _ in range(n_ranks)]
+    inbox = [torch.zeros(total * 5 + 8, dtype=torch.int16, device="cuda") for _ in range(n_ranks)]
+    peers = pcs.ShardPeers()
+    peers.n_ranks, peers.rank, peers.capacity_records = n_ranks, 0, total
+    for r in range(n_ranks):
+        peers.inbox_dev[r], peers.cursor_dev[r], peers.zhist_dev[r] = inbox[r].data_ptr(), cur[r].data_ptr(), zh[r].data_ptr()
+    for r in range(n_ranks):
+        c.shard_hist_dev(d_rec[r].data_ptr(), sizes[r], leaf, zh[r].data_ptr(), cur[r].data_ptr(), cs)
+    splits = torch.zeros(n_ranks + 1, dtype=torch.int32, device="cuda")
+    zslab = torch.zeros((zbins + 15) & ~15, dtype=torch.uint8, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    c.shard_plan_dev(peers, leaf, splits.data_ptr(), zslab.data_ptr(), cs)
+    for r in range(n_ranks):
+        c.shard_scatter_dev(d_rec[r].data_ptr(), sizes[r], leaf, zslab.data_ptr(), peers, err.data_ptr(), cs)
+    out = torch.zeros(total * 5, dtype=torch.int16, device="cuda")
+    cnt = torch.zeros(n_ranks, dtype=torch.int32, device="cuda")
+    got = []
+    for r in range(n_ranks):
+        c.voxel_merge_counted_async_dev(inbox[r].data_ptr(), total, cur[r].data_ptr(), leaf, out.data_ptr(), cnt.data_ptr() + 4 * r, cs)
+        torch.cuda.synchronize()
+        nv = int(cnt[r].item())
+        assert nv >= 0
+        got.append(out[: nv * 5].cpu().numpy().reshape(-1, 5).copy())
+    assert int(err.item()) == 0
+    allrec = np.concatenate(recs)
+    kz = np.floor_divide(allrec[:, 2].astype(np.int32), leaf)
+    sp = splits.cpu().numpy()
+    assert sp[0] == kz.min() and sp[-1] == kz.max() + 1 and np.all(np.diff(sp) >= 0)
+    fill = [int(x.item()) for x in cur]
+    assert fill == [int(((kz >= sp[r]) & (kz < sp[r + 1])).sum()) for r in range(n_ranks)] and sum(fill) == total
+    if n_ranks > 1:
+        assert max(fill) < 2.0 * total / n_ranks + 0.4 * total      # equal population up to whole planes (one is crowded)
+    assert np.array_equal(np.concatenate(got), R.voxel_merge(allrec, leaf))
+    c.close()

@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only-voxel-variant", type=int, default=-1, help="time only this voxel_variant (for ncu runs)")
     ap.add_argument("--skip-stitch", action="store_true", help="voxel merge only")
+    ap.add_argument("--scene", default="noise", choices=["noise", "smooth"],
+                    help="depth noise: 400 mm (default: ~0.84 voxels per point, the merge's worst case) or 5 mm (a surface)")
     a = ap.parse_args()
     ctx = pcs.Context(device=0, max_streams=a.cams)
     cs = torch.cuda.current_stream().cuda_stream
@@ -47,7 +49,8 @@ def main():
     pays, jobs, keep = [], [], []
     for c in range(a.cams):
         ctx.set_stream(c, pcs.stream_desc(W, H, tf=synth.TF_STITCH[c % 8], translation=synth.D2C_BASELINE))
-        z = torch.from_numpy(synth.depth_frame(W, H, c, 0).view(np.int16)).cuda()
+        z = torch.from_numpy(synth.depth_frame(W, H, c, 0, noise_mm=synth.SMOOTH_NOISE_MM if a.scene == "smooth"
+                                               else synth.NOISE_MM).view(np.int16)).cuda()
         col = torch.from_numpy(synth.color_frame(W, H, c, 0)).cuda()
         p = torch.zeros(N * 5, dtype=torch.int16, device="cuda")
         keep.append((z, col))
@@ -61,7 +64,7 @@ def main():
     cloud = torch.zeros(total * 8, dtype=torch.float32, device="cuda")
     ptrs, ns = [p.data_ptr() for p in pays], [N * 5] * a.cams
     tfs = [synth.TF_STITCH[c % 8] for c in range(a.cams)]
-    res = {"cams": a.cams, "points": total}
+    res = {"cams": a.cams, "points": total, "scene": a.scene}
     if not a.skip_stitch:
         for d in (1, 2, 4):
             ms = timed(lambda: ctx.stitch_raw_dev(ptrs, ns, d, st.data_ptr() + 12, total * 10 + 4, cs), a.iters)
