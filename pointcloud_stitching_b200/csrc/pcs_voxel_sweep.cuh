@@ -64,7 +64,8 @@ struct SweepPlan {
     int m;            // points to sort (== n without a slab filter)
     int passes, n_tiles, n_chunks;
     int status;       // 0, or -4 when the (key, slot) word does not fit 64 bits
-    int pad[3];
+    int pre;          // 1: runs of neighbouring same-voxel points are merged into one sort element (m counts runs)
+    int pad[2];
 };
 constexpr int SW_PLAN_SLOTS = 8;     // one per context (contexts sharing a slot must not merge concurrently)
 __constant__ SweepPlan c_sweep_plan[SW_PLAN_SLOTS];
@@ -108,7 +109,7 @@ __device__ __forceinline__ int sw_half(const uint32_t (&w)[20], int h) {   // ha
 }
 
 // ---- 0. occupied box, slab population, optional histogram over qz ---------------------------
-// bounds[0..2] = min qx, qy, qz; bounds[3..5] = max; bounds[6] = points inside the slab.
+// bounds[0..2] = min qx, qy, qz; bounds[3..5] = max; bounds[6] = points inside the slab; bounds[7] = runs (see below).
 // zhist (HIST): points per qz plane over ALL points (the plan for cutting slabs).
 template <bool HIST>
 __global__ void __launch_bounds__(SW_KH_THREADS)
@@ -116,15 +117,15 @@ sw_bounds(const int16_t *__restrict__ rec, int n, SweepGeom g, uint32_t *__restr
           uint32_t *__restrict__ zhist, int zbins, int zhist_in_smem, const int32_t *__restrict__ n_dev = nullptr) {
     extern __shared__ uint32_t sw_zh[];
     if (n_dev) n = max(0, min(n, *n_dev));       // the point count lives on the device (an inbox filled by peers)
-    __shared__ uint32_t red[7];
-    if (threadIdx.x < 7) red[threadIdx.x] = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
+    __shared__ uint32_t red[8];
+    if (threadIdx.x < 8) red[threadIdx.x] = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
     uint32_t *zh = (HIST && zhist_in_smem) ? sw_zh : zhist;
     if (HIST && zhist_in_smem)
         for (int k = threadIdx.x; k < zbins; k += SW_KH_THREADS) sw_zh[k] = 0;
     __syncthreads();
     const bool aligned = (((uintptr_t)rec) & 15) == 0;
     const int n_tiles = (n + SW_KH_TILE - 1) / SW_KH_TILE;
-    uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0, 0, 0}, inside = 0;
+    uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0, 0, 0}, inside = 0, heads = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int first = tile * SW_KH_TILE + threadIdx.x * SW_KH_ITEMS;
         const int cnt = max(0, min(SW_KH_ITEMS, n - first));
@@ -132,16 +133,23 @@ sw_bounds(const int16_t *__restrict__ rec, int n, SweepGeom g, uint32_t *__restr
         uint32_t w[20];
         sw_load8(rec, n, first, cnt == SW_KH_ITEMS && aligned, w);
         uint32_t prev = 0, run = 0;
+        uint32_t lx = 0, ly = 0, lz = 0;
+        bool lin = false;        // the previous item of this thread lies inside the slab (and its voxel is lx, ly, lz)
 #pragma unroll
         for (int k = 0; k < SW_KH_ITEMS; ++k) {
             if (k < cnt) {
                 const uint32_t qx = sw_q(sw_half(w, 5 * k), g), qy = sw_q(sw_half(w, 5 * k + 1), g),
                                qz = sw_q(sw_half(w, 5 * k + 2), g);
-                if ((int)qz >= g.z_lo && (int)qz < g.z_hi) {
+                const bool in = (int)qz >= g.z_lo && (int)qz < g.z_hi;
+                if (in) {
                     mn[0] = min(mn[0], qx); mn[1] = min(mn[1], qy); mn[2] = min(mn[2], qz);
                     mx[0] = max(mx[0], qx); mx[1] = max(mx[1], qy); mx[2] = max(mx[2], qz);
                     ++inside;
+                    // a run = consecutive items of one thread in the same voxel (neighbouring pixels of a surface):
+                    // sw_keys_hist can merge a run into one sort element
+                    if (!(lin && qx == lx && qy == ly && qz == lz)) ++heads;
                 }
+                lin = in; lx = qx; ly = qy; lz = qz;
                 if (HIST) {
                     if (run && qz == prev) {
                         ++run;
@@ -161,6 +169,7 @@ sw_bounds(const int16_t *__restrict__ rec, int n, SweepGeom g, uint32_t *__restr
         mx[a] = __reduce_max_sync(0xffffffffu, mx[a]);
     }
     inside = __reduce_add_sync(0xffffffffu, inside);
+    heads = __reduce_add_sync(0xffffffffu, heads);
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -168,11 +177,12 @@ sw_bounds(const int16_t *__restrict__ rec, int n, SweepGeom g, uint32_t *__restr
             atomicMax(red + 3 + a, mx[a]);
         }
         atomicAdd(red + 6, inside);
+        atomicAdd(red + 7, heads);
     }
     __syncthreads();
     if (threadIdx.x < 3) atomicMin(bounds + threadIdx.x, red[threadIdx.x]);
     else if (threadIdx.x < 6) atomicMax(bounds + threadIdx.x, red[threadIdx.x]);
-    else if (threadIdx.x == 6 && red[6]) atomicAdd(bounds + 6, red[6]);
+    else if (threadIdx.x < 8 && red[threadIdx.x]) atomicAdd(bounds + threadIdx.x, red[threadIdx.x]);
     if (HIST && zhist_in_smem)
         for (int k = threadIdx.x; k < zbins; k += SW_KH_THREADS) {
             const uint32_t v = sw_zh[k];
@@ -187,13 +197,23 @@ __device__ __forceinline__ int sw_bits_for_dev(unsigned long long count) {     /
     return b;
 }
 __global__ void sw_plan(const uint32_t *__restrict__ bounds, SweepGeom base, int n, int slab, int tile, int bits,
-                        SweepPlan *__restrict__ plan, int32_t *__restrict__ nv_out) {
+                        int prereduce, SweepPlan *__restrict__ plan, int32_t *__restrict__ nv_out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     SweepPlan p;
     p.g = base;
-    p.pad[0] = p.pad[1] = p.pad[2] = 0;
+    p.pad[0] = p.pad[1] = 0;
     p.status = 0;
+    p.pre = 0;
     p.m = (int)bounds[6];
+    // Pre-reduction: raster neighbours on a surface share a voxel; when merging the runs inside every thread's eight
+    // records drops at least 10 % of the elements, sort the runs (their partial sums ride in the gather word: count 4
+    // bits, three colour sums of 11 bits, three offset sums of off_bits + 3 bits <= 64 for leaf <= 64 mm)
+    const int heads = (int)bounds[7];
+    if (prereduce && p.m > 0 && p.m <= n && heads > 0 && heads <= p.m && base.off_bits <= 6 &&
+        (long long)heads * 10 <= (long long)p.m * 9) {
+        p.pre = 1;
+        p.m = heads;
+    }
     p.passes = p.n_tiles = p.n_chunks = 0;
     if (p.m > 0 && p.m <= n) {
         SweepGeom &g = p.g;
@@ -203,7 +223,7 @@ __global__ void sw_plan(const uint32_t *__restrict__ bounds, SweepGeom base, int
         g.mdx = g.dx > 1 ? ~0ull / g.dx + 1ull : 0ull;
         g.mdy = g.dy > 1 ? ~0ull / g.dy + 1ull : 0ull;
         const unsigned long long dz = (unsigned long long)bounds[5] - bounds[2] + 1;
-        g.idx_bits = sw_bits_for_dev((unsigned long long)(slab ? p.m : n));
+        g.idx_bits = sw_bits_for_dev((unsigned long long)((slab || p.pre) ? p.m : n));
         const int key_bits = sw_bits_for_dev((unsigned long long)g.dx * g.dy * dz);   // < 2^48 always
         // the multiply-high divisions in sw_emit are exact while key * d stays below 2^64
         const double vol = (double)g.dx * (double)g.dy * (double)dz * (double)max(g.dx, g.dy);
@@ -217,6 +237,7 @@ __global__ void sw_plan(const uint32_t *__restrict__ bounds, SweepGeom base, int
     } else if (p.m > n) {
         p.status = -2;
     }
+    if (p.status != 0) p.pre = 0;
     *plan = p;
     if (p.status != 0 || p.m == 0) *nv_out = p.status;     // nothing else will write the result
 }
@@ -227,7 +248,10 @@ __global__ void sw_plan(const uint32_t *__restrict__ bounds, SweepGeom base, int
 // point's slot is its index; with one, the tile's survivors take consecutive slots reserved with one
 // atomicAdd per tile (their order is irrelevant: the slot only ties the sort word to its gather word,
 // and the per-voxel sums are integers).
-template <int BITS, bool FILTER>
+// PRE: runs of consecutive same-voxel items inside a thread's eight records become ONE sort element whose gather
+// word carries the run's partial sums: count (4 bits) | R, G, B sums (11 bits each) | x, y, z offset sums (off_bits + 3
+// bits each).  The host launches both forms; the plan (made on the device) says which one runs.
+template <int BITS, bool FILTER, bool PRE>
 __global__ void __launch_bounds__(SW_KH_THREADS)
 sw_keys_hist(const int16_t *__restrict__ rec, int n, int plan_slot,
              uint64_t *__restrict__ words, uint64_t *__restrict__ pay, uint32_t *__restrict__ ghist,
@@ -237,7 +261,7 @@ sw_keys_hist(const int16_t *__restrict__ rec, int n, int plan_slot,
     const SweepPlan &plan = c_sweep_plan[plan_slot];
     const SweepGeom &g = plan.g;
     const int passes = plan.passes;
-    if (passes == 0) return;
+    if (passes == 0 || (plan.pre != 0) != PRE) return;
     extern __shared__ uint32_t sw_hist[];    // [passes][BINS]
     __shared__ uint32_t warp_cnt[SW_KH_THREADS / 32], s_base;
     for (int k = threadIdx.x; k < passes * BINS; k += SW_KH_THREADS) sw_hist[k] = 0;
@@ -251,26 +275,47 @@ sw_keys_hist(const int16_t *__restrict__ rec, int n, int plan_slot,
         uint32_t w[20];
         if (cnt > 0) sw_load8(rec, n, first, cnt == SW_KH_ITEMS && aligned, w);
         uint64_t word[SW_KH_ITEMS], pw[SW_KH_ITEMS];
-        uint32_t keep = 0;     // bit k: item k exists and lies inside the slab
+        uint32_t keep = 0;     // bit k: item k exists and lies inside the slab (PRE: and starts a run)
+        uint32_t cont = 0;     // PRE, bit k: item k continues the run of item k - 1
+        const int pw_ = g.off_bits + 3;
 #pragma unroll
         for (int k = 0; k < SW_KH_ITEMS; ++k) {
             if (k < cnt) {
                 const int x = sw_half(w, 5 * k), y = sw_half(w, 5 * k + 1), z = sw_half(w, 5 * k + 2);
                 const uint32_t s3 = (uint32_t)sw_half(w, 5 * k + 3) & 0xFFFFu, s4 = (uint32_t)sw_half(w, 5 * k + 4) & 0xFFu;
                 const uint32_t qx = sw_q(x, g), qy = sw_q(y, g), qz = sw_q(z, g);
-                if (!FILTER || ((int)qz >= g.z_lo && (int)qz < g.z_hi)) keep |= 1u << k;
+                if (!(FILTER || PRE) || ((int)qz >= g.z_lo && (int)qz < g.z_hi)) keep |= 1u << k;
                 word[k] = ((uint64_t)(qz - (uint32_t)g.z0) * g.dy + (uint64_t)(qy - (uint32_t)g.y0)) * g.dx +
                           (uint64_t)(qx - (uint32_t)g.x0);
                 const uint64_t ox = (uint64_t)(uint32_t)(x + g.bias - g.leaf * (int)qx),
                                oy = (uint64_t)(uint32_t)(y + g.bias - g.leaf * (int)qy),
                                oz = (uint64_t)(uint32_t)(z + g.bias - g.leaf * (int)qz);
-                pw[k] = (uint64_t)(s3 | (s4 << 16)) | (ox << 24) | (oy << (24 + g.off_bits)) | (oz << (24 + 2 * g.off_bits));
+                if (PRE) {
+                    pw[k] = 1ull | ((uint64_t)(s3 & 0xFFu) << 4) | ((uint64_t)(s3 >> 8) << 15) | ((uint64_t)s4 << 26) |
+                            (ox << 37) | (oy << (37 + pw_)) | (oz << (37 + 2 * pw_));
+                    // the same voxel as the item before (both inside): equal keys <=> equal voxels inside the box
+                    if (k > 0 && ((keep >> (k - 1)) & 3u) == 3u && word[k] == word[k - 1]) cont |= 1u << k;
+                } else {
+                    pw[k] = (uint64_t)(s3 | (s4 << 16)) | (ox << 24) | (oy << (24 + g.off_bits)) | (oz << (24 + 2 * g.off_bits));
+                }
             } else {
                 word[k] = 0; pw[k] = 0;
             }
         }
+        if (PRE) {
+            // back to front: a run's sums collect in its first item (field widths leave room for eight points)
+            uint64_t acc = 0;
+#pragma unroll
+            for (int k = SW_KH_ITEMS - 1; k >= 0; --k) {
+                if ((keep >> k) & 1u) {
+                    acc += pw[k];
+                    if (!((cont >> k) & 1u)) { pw[k] = acc; acc = 0; }
+                }
+            }
+            keep &= ~cont;
+        }
         uint32_t slot0 = (uint32_t)first;     // slot of this thread's first surviving item
-        if (FILTER) {
+        if (FILTER || PRE) {
             const uint32_t c = __popc(keep);
             uint32_t inc = c;
 #pragma unroll
@@ -291,7 +336,7 @@ sw_keys_hist(const int16_t *__restrict__ rec, int n, int plan_slot,
             __syncthreads();
             slot0 = s_base + before + inc - c;
         }
-        if (!FILTER && cnt == SW_KH_ITEMS) {
+        if (!(FILTER || PRE) && cnt == SW_KH_ITEMS) {
 #pragma unroll
             for (int k = 0; k < SW_KH_ITEMS; ++k) word[k] = (word[k] << g.idx_bits) | (uint64_t)(slot0 + k);
             uint4 *o = reinterpret_cast<uint4 *>(words + first), *q = reinterpret_cast<uint4 *>(pay + first);
@@ -351,7 +396,7 @@ sw_keys_hist(const int16_t *__restrict__ rec, int n, int plan_slot,
             const uint32_t tot = seg_end - (inc - run);
             if (head && tot) atomicAdd(h + prev, tot);
         }
-        if (FILTER) __syncthreads();   // warp_cnt / s_base are rewritten by the next tile
+        if (FILTER || PRE) __syncthreads();   // warp_cnt / s_base are rewritten by the next tile
     }
     __syncthreads();
     for (int k = threadIdx.x; k < passes * BINS; k += SW_KH_THREADS) {
@@ -740,6 +785,8 @@ sw_reduce(const uint64_t *__restrict__ w0, const uint64_t *__restrict__ w1, cons
           uint32_t *__restrict__ slots, uint64_t *__restrict__ slotkey, int16_t *__restrict__ out) {
     const SweepPlan &plan = c_sweep_plan[plan_slot];
     const SweepGeom &g = plan.g;
+    // the host launches both forms: packed sums need single points of a small leaf, merged runs need the wide scan
+    if (PACKED != (plan.pre == 0 && g.off_bits <= 5)) return;
     const uint64_t *__restrict__ sorted = (plan.passes & 1) ? w1 : w0;
     const int n = plan.m, n_chunks = plan.n_chunks;
     const int lane = threadIdx.x & 31;
@@ -800,7 +847,16 @@ sw_reduce(const uint64_t *__restrict__ w0, const uint64_t *__restrict__ w1, cons
             v[0] = A & 1023u; v[1] = (A >> 10) & 1023u; v[2] = A >> 20;
             v[3] = B & 8191u; v[4] = (B >> 13) & 8191u; v[6] = B >> 26; v[5] = Cc;
         } else {
-            if (valid) {
+            if (valid && plan.pre) {         // a merged run: count | R, G, B sums | offset sums
+                const int pw_ = g.off_bits + 3;
+                const uint32_t pm = (1u << pw_) - 1;
+                const uint64_t offs = pw[r] >> 37;
+                v[0] = (uint32_t)offs & pm;
+                v[1] = (uint32_t)(offs >> pw_) & pm;
+                v[2] = (uint32_t)(offs >> (2 * pw_)) & pm;
+                v[3] = (uint32_t)(pw[r] >> 4) & 2047u; v[4] = (uint32_t)(pw[r] >> 15) & 2047u;
+                v[5] = (uint32_t)(pw[r] >> 26) & 2047u; v[6] = (uint32_t)pw[r] & 15u;
+            } else if (valid) {
                 const uint32_t lo = (uint32_t)pw[r];
                 const uint64_t offs = pw[r] >> 24;
                 v[0] = (uint32_t)offs & om;
@@ -1046,7 +1102,8 @@ inline int voxel_merge_sweep_enqueue(VoxelScratch &s, const int16_t *rec, int n,
     const int kh_grid = std::min(kh_tiles, std::max(1, sm_count) * 8);
     sw_bounds<false><<<kh_grid, SW_KH_THREADS, 0, cs>>>(rec, n, g, bounds, nullptr, 0, 0, n_dev);
     // (with a device-side count the slots are the record indices below that count: index bits from m, as for a slab)
-    sw_plan<<<1, 32, 0, cs>>>(bounds, g, n, (slab || n_dev) ? 1 : 0, Cfg::TILE, BITS, d_plan, nv_dev);
+    static const int prereduce = pipe_knob("PCS_SW_PREREDUCE", 1, 0, 1);     // 0: never merge runs before the sort
+    sw_plan<<<1, 32, 0, cs>>>(bounds, g, n, (slab || n_dev) ? 1 : 0, Cfg::TILE, BITS, prereduce, d_plan, nv_dev);
     if (cudaMemcpyToSymbolAsync(c_sweep_plan, d_plan, sizeof(SweepPlan), (size_t)plan_slot * sizeof(SweepPlan),
                                 cudaMemcpyDeviceToDevice, cs) != cudaSuccess)
         return -2;
@@ -1057,10 +1114,13 @@ inline int voxel_merge_sweep_enqueue(VoxelScratch &s, const int16_t *rec, int n,
              *gstatus = (uint32_t *)(s.buf + o_gstat),
              *chunk_off = (uint32_t *)(s.buf + o_off), *ownerpos = (uint32_t *)(s.buf + o_owner);
     uint64_t *info = (uint64_t *)(s.buf + o_info), *slotkey = (uint64_t *)(s.buf + o_skey);
+    // one of the two runs (the plan decides on the device whether runs are merged)
     if (slab)
-        sw_keys_hist<BITS, true><<<kh_grid, SW_KH_THREADS, (size_t)passes_max * BINS * 4, cs>>>(rec, n, plan_slot, w0, pay, ghist, slot_counter, n_dev);
+        sw_keys_hist<BITS, true, false><<<kh_grid, SW_KH_THREADS, (size_t)passes_max * BINS * 4, cs>>>(rec, n, plan_slot, w0, pay, ghist, slot_counter, n_dev);
     else
-        sw_keys_hist<BITS, false><<<kh_grid, SW_KH_THREADS, (size_t)passes_max * BINS * 4, cs>>>(rec, n, plan_slot, w0, pay, ghist, slot_counter, n_dev);
+        sw_keys_hist<BITS, false, false><<<kh_grid, SW_KH_THREADS, (size_t)passes_max * BINS * 4, cs>>>(rec, n, plan_slot, w0, pay, ghist, slot_counter, n_dev);
+    if (prereduce)
+        sw_keys_hist<BITS, true, true><<<kh_grid, SW_KH_THREADS, (size_t)passes_max * BINS * 4, cs>>>(rec, n, plan_slot, w0, pay, ghist, slot_counter, n_dev);
     sw_hist_scan<BITS><<<passes_max, BINS, 0, cs>>>(ghist);
     static const bool ballot = pipe_knob("PCS_SW_BALLOT", 1, 0, 1) != 0;     // 0: MATCH.ANY ranking (tuning knob)
 #ifdef PCS_SW_PROBES      // timing probes skip phases of sw_pass (WRONG results): only in builds made for tools/probe_vox.py
@@ -1083,7 +1143,7 @@ inline int voxel_merge_sweep_enqueue(VoxelScratch &s, const int16_t *rec, int n,
     sw_chunk_scan<<<1, 1024, 0, cs>>>(info, plan_slot, chunk_off, ownerpos, nv_dev);
     if (g.off_bits <= 5)
         sw_reduce<true><<<cblocks, 256, 0, cs>>>(wa, wb, pay, plan_slot, chunk_off, ownerpos, slots, slotkey, out);
-    else
+    if (g.off_bits > 5 || prereduce)
         sw_reduce<false><<<cblocks, 256, 0, cs>>>(wa, wb, pay, plan_slot, chunk_off, ownerpos, slots, slotkey, out);
     sw_finalize_open<<<(chunks_max + 255) / 256, 256, 0, cs>>>(info, chunk_off, slots, slotkey, plan_slot, out);
     sw_result<<<1, 32, 0, cs>>>(nv_dev, err, plan_slot);

@@ -504,3 +504,41 @@ def test_shard_before_exchange_kernels_on_one_gpu(R, n_ranks):
         assert max(fill) < 2.0 * total / n_ranks + 0.4 * total      # equal population up to whole planes (one is crowded)
     assert np.array_equal(np.concatenate(got), R.voxel_merge(allrec, leaf))
     c.close()
+
+
+@pytest.mark.parametrize("variant", [0, 4], ids=["sort_with_merged_runs", "msd"])
+def test_voxel_merge_of_a_smooth_scene(R, variant):
+    """A surface as a depth camera sees it (5 mm noise): raster neighbours share voxels, so the sort merges the runs
+    inside every thread's eight records before sorting (sw_plan decides on the device).  K1 records of two cameras,
+    the full cloud, a z slab of it, and the asynchronous call -- all against the oracle."""
+    w, h, cams = 848, 480, 2
+    c = pcs.Context(device=0, max_streams=cams, voxel_variant=variant)
+    cal = oracle.make_calib(w, h, translation=synth.D2C_BASELINE)
+    recs = [R.frame(cal, synth.depth_frame(w, h, cam, 1, noise_mm=synth.SMOOTH_NOISE_MM), synth.color_frame(w, h, cam, 1), 3,
+                    w * 3, synth.TF_STITCH[cam]) for cam in range(cams)]
+    rec = np.concatenate(recs)
+    want = R.voxel_merge(rec, 10)
+    assert len(want) < 0.6 * len(rec)                     # several points per voxel
+    n = len(rec)
+    d = torch.from_numpy(rec.reshape(-1).copy()).cuda()
+    out = torch.zeros(n * 5, dtype=torch.int16, device="cuda")
+    cs = torch.cuda.current_stream().cuda_stream
+    nv = c.voxel_merge_dev(d.data_ptr(), n, 10, out.data_ptr(), cs)
+    torch.cuda.synchronize()
+    assert nv == len(want) and np.array_equal(out[: nv * 5].cpu().numpy().reshape(-1, 5), want)
+    kz = np.floor_divide(rec[:, 2].astype(np.int32), 10)
+    lo, hi = int(np.percentile(kz, 25)), int(np.percentile(kz, 80))
+    nv = c.voxel_merge_slab_dev(d.data_ptr(), n, 10, lo, hi, out.data_ptr(), cs)
+    torch.cuda.synchronize()
+    want_slab = R.voxel_merge(rec[(kz >= lo) & (kz < hi)], 10)
+    assert nv == len(want_slab) and np.array_equal(out[: nv * 5].cpu().numpy().reshape(-1, 5), want_slab)
+    if variant == 0:
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        c.voxel_merge_async_dev(d.data_ptr(), n, 10, out.data_ptr(), cnt.data_ptr(), cs)
+        torch.cuda.synchronize()
+        assert int(cnt.item()) == len(want) and np.array_equal(out[: len(want) * 5].cpu().numpy().reshape(-1, 5), want)
+        # other leaf sizes with merged runs: 3 mm (2-bit offsets) and 40 mm (6-bit offsets: the widest gather word)
+        for leaf in (3, 40):
+            got = c.voxel_merge(rec, leaf)
+            assert np.array_equal(got, R.voxel_merge(rec, leaf)), leaf
+    c.close()
