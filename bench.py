@@ -689,7 +689,14 @@ def main():
     # one k1_pipe launch there); for N > 1 the step also holds the exchange, so the K1-only loop
     launch_ms = (ms_step if world == 1 else ms_kernel_step) / launches_per_step_local
     peak, peak_src = measured_peak()
-    color_bytes = ch * cw * 3 / NPTS          # colour bytes per depth pixel (3 when the frames have the same size)
+    # colour bytes per depth pixel: the rows the taps can land in.  Same-size frames: every row, 3 B/px.  A colour frame
+    # of another size behind a pure x baseline: depth row y taps colour row floor((y - ppy) / fy * cfy + cppy + .5) whatever
+    # the depth (the library proves it per stream and reads only those rows), so the rows in between are never needed
+    if args.tex == "color1080p":
+        tapped = len({int(np.floor((y - (H - 1) / 2) / (W / 2) * (cw / 2) + (ch - 1) / 2 + 0.5)) for y in range(H)})
+    else:
+        tapped = ch
+    color_bytes = tapped * cw * 3 / NPTS
     alg_bpp = 2 + color_bytes + 10
     alg_bytes_launch = alg_bpp * S * F * NPTS / launches_per_step_local
     achieved = alg_bytes_launch / (launch_ms * 1e-3) / 1e9
@@ -697,7 +704,10 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel": "k1_pipe" if args.variant != 1 else "k1_direct",
-                "algorithmic_bytes_per_point": alg_bpp, "algorithmic_bytes_per_launch": alg_bytes_launch, "launch_ms": launch_ms}
+                "algorithmic_bytes_per_point": alg_bpp, "algorithmic_bytes_per_launch": alg_bytes_launch, "launch_ms": launch_ms,
+                "colour_rows_tapped": tapped, "colour_rows": ch,
+                "frac_if_whole_colour_frame_counted": (2 + ch * cw * 3 / NPTS + 10) * S * F * NPTS / launches_per_step_local
+                / (launch_ms * 1e-3) / 1e9 / peak}
 
     # ---- sustained: the same K1 step back to back for >= 2 s (power-capped clocks), beside the burst figure
     sustained = None

@@ -46,6 +46,8 @@ struct StreamState {
     int32_t *h_count = nullptr;     // pinned
     DevJob *d_job = nullptr;
     size_t cap_pts = 0, cap_color = 0;
+    int32_t *d_rowmap = nullptr;    // TEX_TRANSLATE_X row map (depth row -> colour row), see make_rowmap
+    size_t cap_rowmap = 0;
     // vertices path
     float *d_xyz = nullptr, *d_uv = nullptr;
     int16_t *d_vpayload = nullptr;
@@ -192,6 +194,28 @@ int pick_tex_mode(const pcs_stream_desc &d) {
                         d.depth.fy == d.color.fy && d.depth.ppy == d.color.ppy;
     if (same_v && sane && d.d2c_translation[1] == 0.f && d.d2c_translation[2] == 0.f) return TEX_TRANSLATE_X;
     return TEX_TRANSLATE;
+}
+
+// R = I and T = (tx, 0, 0): t1 = p1 and t2 = depth exactly, so the tap ROW of a valid pixel depends on its own row and
+// (through rounding only) on the depth value:  py = fl(fl(fl(fl(depth * ny) / depth) * cfy) + cppy), tap =
+// trunc(fma(fl(py / CH), CH, .5)).  In real arithmetic that is r(y) = (y - ppy) / fy * cfy + cppy; the float chain strays
+// from it by < (|r - cppy| * 5 + |r| * 2) * 2^-24 + ulp(|r|) / 2  (~4.5e-4 px at r ~ 1000: oracle/SPEC.md s1 gives the same
+// argument for equal intrinsics).  If r(y) + 0.5 keeps a distance of 1e-3 + |r| * 2e-6 (> 3 x that bound) from every
+// integer for EVERY row, the tap row is floor(r(y) + 0.5) clamped, whatever the depth: a table.  Colour frames of another
+// size (1280x720 depth + 1920x1080 colour, what the reference records: src/pcs-camera-grab-frames.cpp:69-70) then run
+// through the row-exact kernel path instead of the windowed one.  tests/test_k1_gpu.py sweeps every z16 at every row.
+bool make_rowmap(const pcs_stream_desc &d, std::vector<int32_t> &tab) {
+    const int H = d.depth.height, CH = d.color.height;
+    if (H < 1 || H > 8192 || CH < 1 || CH > 8192) return false;
+    tab.resize(H);
+    for (int y = 0; y < H; ++y) {
+        const double r = ((double)y - (double)d.depth.ppy) / (double)d.depth.fy * (double)d.color.fy + (double)d.color.ppy;
+        const double t = r + 0.5, k = std::floor(t);
+        const double dist = std::min(t - k, k + 1.0 - t);
+        if (!(dist >= 1e-3 + std::fabs(r) * 2e-6) || !(std::fabs(r) < 1e6)) return false;
+        tab[y] = (int32_t)std::min<double>(std::max<double>(k, 0.0), (double)(CH - 1));
+    }
+    return true;
 }
 
 void digest(const pcs_stream_desc &d, StreamParams &p) {
@@ -380,7 +404,7 @@ void pcs_b200_destroy(pcs_ctx *ctx) {
         StreamState &s = ctx->streams[i];
         if (s.cs) { cudaStreamSynchronize(s.cs); cudaStreamDestroy(s.cs); }
         cudaFree(s.d_z16); cudaFree(s.d_color); cudaFree(s.d_payload); cudaFree(s.d_dense);
-        cudaFree(s.d_keep); cudaFree(s.d_tiles); cudaFree(s.d_count); cudaFree(s.d_job);
+        cudaFree(s.d_keep); cudaFree(s.d_tiles); cudaFree(s.d_count); cudaFree(s.d_job); cudaFree(s.d_rowmap);
         cudaFree(s.d_xyz); cudaFree(s.d_uv); cudaFree(s.d_vpayload);
         cudaFree(s.d_cdense); cudaFree(s.d_ckeep); cudaFree(s.d_ctiles);
         if (s.h_count) cudaFreeHost(s.h_count);
@@ -427,6 +451,23 @@ int pcs_b200_set_stream(pcs_ctx *ctx, int stream, const pcs_stream_desc *desc) {
     }
     s.desc = d;
     digest(d, s.params);
+    // colour of another size / other vertical intrinsics behind a pure x baseline: row-exact through a proven row map
+    if (s.params.tex_mode == TEX_TRANSLATE && d.d2c_translation[1] == 0.f && d.d2c_translation[2] == 0.f &&
+        d.depth.width <= 4096 && d.depth.fx >= 16.f && d.depth.fy >= 16.f && d.depth.fx <= 65536.f && d.depth.fy <= 65536.f &&
+        d.depth_scale >= 1e-6f && d.depth_scale <= 1.0f) {
+        std::vector<int32_t> tab;
+        if (make_rowmap(d, tab)) {
+            if (tab.size() > s.cap_rowmap) {
+                cudaFree(s.d_rowmap);
+                s.d_rowmap = nullptr; s.cap_rowmap = 0;
+                if (cudaMalloc(&s.d_rowmap, tab.size() * 4 + 64) != cudaSuccess) { cudaGetLastError(); return fail(ctx, PCS_ERR_NOMEM, "cudaMalloc failed"); }
+                s.cap_rowmap = tab.size();
+            }
+            CU(ctx, cudaMemcpy(s.d_rowmap, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+            s.params.tex_mode = TEX_TRANSLATE_X;
+            s.params.rowmap = s.d_rowmap;
+        }
+    }
     s.configured = true;
     CU(ctx, cudaMemcpy(ctx->d_params + stream, &s.params, sizeof(StreamParams), cudaMemcpyHostToDevice));
     return PCS_OK;

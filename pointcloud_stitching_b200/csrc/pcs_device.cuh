@@ -32,6 +32,10 @@ struct StreamParams {
     float tf[12];                   // rows 0..2 of the camera -> world 4x4
     int cutoff, lane_rev;
     float z_lo, z_hi, x_lo, x_hi;
+    // TEX_TRANSLATE_X with a colour frame of another size / other vertical intrinsics: the colour row every depth
+    // row taps (device memory, H entries), proven on the host to be what the exact chain yields for every depth
+    // value (pcs_abi.cu make_rowmap); NULL when the tap row is the pixel's own row
+    const int32_t *rowmap;
 };
 
 // x86 CVTTSS2SI semantics: truncate; NaN / out of range -> 0x80000000.
@@ -98,7 +102,7 @@ __device__ __forceinline__ void deproject_tap(const StreamParams &s, uint32_t z1
             u = __fdiv_rn(px, s.cwf);
         }
         xi = tex_to_pixel(u, s.cwf, s.CW - 1);
-        yi = valid ? y : 0;
+        yi = valid ? (s.rowmap ? __ldg(s.rowmap + y) : y) : 0;
         return;
     }
     float u = 0.0f, v = 0.0f;

@@ -188,6 +188,36 @@ def test_every_depth_value_at_every_column(ctx, R, w, h):
                 z.reshape(-1)[bad[0]], bad[0] % w, rec[bad[0]], want[bad[0]])
 
 
+@pytest.mark.parametrize("geom", ["720p_color1080p", "480p_color720p_odd", "480p_color720p_no_map"])
+def test_every_depth_value_at_every_row_with_a_row_map(ctx, R, geom):
+    """Colour of another size behind a pure x baseline runs row-exact through a host-built row map (pcs_abi.cu
+    make_rowmap): the tap row must not depend on the depth value.  Exhaustive: every z16 in 1..65535 at EVERY row
+    (column x of frame f carries depth f * w + x), against the oracle's full chain."""
+    if geom == "720p_color1080p":       # what the reference records (src/pcs-camera-grab-frames.cpp:69-70)
+        w, h, kw = 1280, 720, dict(cw=1920, ch=1080)
+    elif geom == "480p_color720p_odd":  # non-round vertical intrinsics whose rows stay 0.17 px away from a tap boundary
+        w, h, kw = 848, 480, dict(cw=1280, ch=720, dfy=421.3, dppy=236.2, cfy=631.9, cppy=361.1)
+    else:                               # a row comes within 1e-3 px of a boundary: no map, the windowed kernel runs
+        w, h, kw = 848, 480, dict(cw=1280, ch=720, dfy=421.3, dppy=236.2, cfy=633.1, cppy=361.4)
+    cw, ch = kw.pop("cw"), kw.pop("ch")
+    cal, desc = calib_and_desc(w, h, cw, ch, tf=synth.TF_STITCH[2], translation=synth.D2C_BASELINE, **kw)
+    ctx.set_stream(0, desc)
+    col = synth.color_frame(cw, ch, 12, 0)
+    n_frames = -(-65536 // w)
+    jobs = []
+    for f in range(n_frames):
+        z = ((np.arange(w, dtype=np.int64) + f * w) % 65536).astype(np.uint16)
+        jobs.append((0, np.ascontiguousarray(np.repeat(z[None, :], h, axis=0)), col))
+    for lo in range(0, n_frames, 16):
+        chunk = jobs[lo:lo + 16]
+        got = run_batch(ctx, chunk, None)
+        for (_, z, c), (rec, _, _) in zip(chunk, got):
+            want = R.frame(cal, z, c, 3, cw * 3, synth.TF_STITCH[2])
+            bad = np.nonzero((rec != want).any(axis=1))[0]
+            assert bad.size == 0, "z16=%d row=%d: got %s want %s" % (
+                z.reshape(-1)[bad[0]], bad[0] // w, rec[bad[0]], want[bad[0]])
+
+
 def test_heterogeneous_batch(ctx, R):
     # several streams of different geometry and tex mode in one batch
     specs = [dict(w=1280, h=720), dict(w=848, h=480, translation=synth.D2C_BASELINE),
