@@ -248,8 +248,9 @@ PCS_API int pcs_b200_stitch_pcl(pcs_ctx *ctx, const int16_t *const *payload_host
  * brings [int32][records] back.
  *   slot          0 .. PCS_B200_STITCH_SLOTS-1: independent pipelines; a host thread keeps two frames
  *                 in flight by alternating slots (begin(0) begin(1) end(0) begin(0) end(1) ...)
- *   streams       n_cams stream ids (pcs_b200_set_stream), in stitched order; cutoff (-c) streams are
- *                 not supported here (use pcs_b200_send_xyzrgb + pcs_b200_stitch_raw)
+ *   streams       n_cams stream ids (pcs_b200_set_stream), in stitched order.  With a cutoff (-c) stream in the set the
+ *                 record counts only exist on the device: the concat reads them there, and end() fetches the total
+ *                 before the records (one more synchronisation)
  *   z16_host / color_host   n_cams frame pointers each; pinned memory (pcs_b200_host_alloc) lets the
  *                 copies overlap the other slot's work
  *   stitched_cap  bytes available at stitched_host

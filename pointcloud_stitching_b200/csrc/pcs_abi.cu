@@ -79,6 +79,10 @@ struct StitchSlot {
     std::vector<pcs_batch *> cam_batch;       // one launch per camera, on that camera's own stream
     std::vector<cudaStream_t> cam_cs;
     std::vector<long long> cam_off;           // first record of every camera in the stitched payload
+    // -c streams: a camera compacts inside its own slot, the counts stay on the device until the concat has run
+    int32_t *d_counts = nullptr, *d_total = nullptr, *h_total = nullptr;
+    bool counted = false;
+    uint8_t *pending_host = nullptr;
     long long total_pts = 0, out_bytes = 0;
     bool pending = false, per_camera = false;
 };
@@ -423,6 +427,8 @@ void pcs_b200_destroy(pcs_ctx *ctx) {
         if (sl.batch) pcs_b200_batch_destroy(ctx, sl.batch);
         for (auto *b : sl.cam_batch) pcs_b200_batch_destroy(ctx, b);
         for (auto c : sl.cam_cs) { cudaStreamSynchronize(c); cudaStreamDestroy(c); }
+        cudaFree(sl.d_counts); cudaFree(sl.d_total);
+        if (sl.h_total) cudaFreeHost(sl.h_total);
     }
     delete ctx;
 }
@@ -1058,19 +1064,28 @@ static int stitch_slot_prepare(pcs_ctx *ctx, StitchSlot &sl, int n_cams, const i
     for (auto c : sl.cam_cs) cudaStreamSynchronize(c);
     for (auto *b : sl.cam_batch) pcs_b200_batch_destroy(ctx, b);
     sl.cam_batch.clear(); sl.cam_off.clear();
+    cudaFree(sl.d_counts); cudaFree(sl.d_total);
+    sl.d_counts = sl.d_total = nullptr;
     sl.d_z.clear(); sl.d_c.clear(); sl.d_stitched = sl.d_decimated = nullptr; sl.batch = nullptr;
     sl.streams.clear(); sl.gens.clear();
     long long total = 0, out = 0;
+    bool any_cutoff = false;
     for (int i = 0; i < n_cams; ++i) {
         const StreamParams &p = ctx->streams[streams[i]].params;
         total += p.N;
         out += (p.N + downsample - 1) / downsample;
+        any_cutoff = any_cutoff || p.cutoff;
     }
+    sl.counted = any_cutoff;
     if (total * 10 > 0x7fffffffll) return fail(ctx, PCS_ERR_CAPACITY, "stitched payload exceeds int32");
     std::vector<pcs_frame_job> jobs(n_cams);
     auto oom = [&]() { cudaGetLastError(); return fail(ctx, PCS_ERR_NOMEM, "stitch_frames: device allocation failed"); };
     if (cudaMalloc(&sl.d_stitched, (size_t)total * 10 + 32) != cudaSuccess) return oom();
-    if (downsample > 1 && cudaMalloc(&sl.d_decimated, (size_t)out * 10 + 32) != cudaSuccess) return oom();
+    if ((downsample > 1 || any_cutoff) && cudaMalloc(&sl.d_decimated, (size_t)out * 10 + 32) != cudaSuccess) return oom();
+    if (any_cutoff) {
+        if (cudaMalloc(&sl.d_counts, (size_t)n_cams * 4 + 64) != cudaSuccess || cudaMalloc(&sl.d_total, 64) != cudaSuccess) return oom();
+        if (!sl.h_total && cudaHostAlloc(&sl.h_total, 64, cudaHostAllocDefault) != cudaSuccess) return oom();
+    }
     long long off = 0;
     for (int i = 0; i < n_cams; ++i) {
         const StreamParams &p = ctx->streams[streams[i]].params;
@@ -1085,6 +1100,9 @@ static int stitch_slot_prepare(pcs_ctx *ctx, StitchSlot &sl, int n_cams, const i
         jobs[i].z16_dev = z;
         jobs[i].color_dev = c;
         jobs[i].payload_dev = reinterpret_cast<int16_t *>(sl.d_stitched + 16 + off * 10);
+        if (any_cutoff) {          // (a -c camera compacts in place of its dense records: its slot is its payload)
+            jobs[i].count_dev = p.cutoff ? sl.d_counts + i : nullptr;
+        }
         off += p.N;
     }
     // Two pipelines.  per camera (default when nothing is decimated): every camera has its own stream -- frame up,
@@ -1092,7 +1110,7 @@ static int stitch_slot_prepare(pcs_ctx *ctx, StitchSlot &sl, int n_cams, const i
     // up (this is what keeps both directions of the link busy: +9 % over one batched launch + one big copy).
     // batch: all cameras in ONE launch, then (decimation and) one copy.
     static const int pipeline = pipe_knob("PCS_STITCH_PIPELINE", 0, 0, 1);     // 0 = per camera, 1 = batch
-    sl.per_camera = downsample == 1 && pipeline == 0;
+    sl.per_camera = downsample == 1 && pipeline == 0 && !any_cutoff;
     int rc;
     if (sl.per_camera) {
         long long o = 0;
@@ -1133,8 +1151,6 @@ int pcs_b200_stitch_frames_begin(pcs_ctx *ctx, int slot, int n_cams, const int32
     for (int i = 0; i < n_cams; ++i) {
         int rc = check_stream(ctx, streams[i], true);
         if (rc) return rc;
-        if (ctx->streams[streams[i]].params.cutoff)
-            return fail(ctx, PCS_ERR_UNSUPPORTED, "stream %d has cutoff set: use pcs_b200_send_xyzrgb + pcs_b200_stitch_raw", streams[i]);
         if (!z16_host[i] || !color_host[i]) return fail(ctx, PCS_ERR_INVALID, "camera %d: null frame", i);
     }
     StitchSlot &sl = ctx->stitch_slots[slot];
@@ -1167,6 +1183,28 @@ int pcs_b200_stitch_frames_begin(pcs_ctx *ctx, int slot, int n_cams, const int32
     }
     if ((rc = pcs_b200_batch_run(ctx, sl.batch, sl.cs))) return rc;
     const uint8_t *src = sl.d_stitched + 12;
+    if (sl.counted) {
+        // -c: the cameras' record counts only exist on the device.  The concat reads them there; its total comes back
+        // first (4 bytes), the records once end() knows how many there are.
+        CountedTable t{};
+        t.n_cams = n_cams;
+        t.downsample = downsample;
+        long long off = 0;
+        for (int i = 0; i < n_cams; ++i) {
+            const StreamParams &p = ctx->streams[streams[i]].params;
+            t.src[i] = reinterpret_cast<const int16_t *>(sl.d_stitched + 16 + off * 10);
+            t.cnt_dev[i] = p.cutoff ? sl.d_counts + i : nullptr;
+            t.cnt_fixed[i] = p.N;
+            off += p.N;
+        }
+        const int blocks = std::max(1, std::min((int)((sl.out_bytes / 10 + 255) / 256), ctx->sm_count * 8));
+        stitch_counted<<<blocks, 256, 0, sl.cs>>>(t, sl.d_decimated + 12, sl.d_total);
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaMemcpyAsync(sl.h_total, sl.d_total, 4, cudaMemcpyDeviceToHost, sl.cs));
+        sl.pending_host = stitched_host;
+        sl.pending = true;
+        return PCS_OK;
+    }
     if (downsample > 1) {
         // every downsample-th record of each camera (src/pcs-multicamera-client.cpp:388), device to device
         std::vector<const int16_t *> pay(n_cams);
@@ -1200,6 +1238,13 @@ int pcs_b200_stitch_frames_end(pcs_ctx *ctx, int slot) {
         for (size_t i = 0; i < sl.streams.size(); ++i) CU(ctx, cudaStreamSynchronize(sl.cam_cs[i]));
     } else {
         CU(ctx, cudaStreamSynchronize(sl.cs));
+    }
+    if (sl.counted) {
+        const int32_t bytes = *sl.h_total;
+        if (bytes < 0 || bytes > sl.out_bytes) return fail(ctx, PCS_ERR_CUDA, "stitch_frames: inconsistent record count");
+        CU(ctx, cudaMemcpyAsync(sl.pending_host, sl.d_decimated + 12, (size_t)bytes + 4, cudaMemcpyDeviceToHost, sl.cs));
+        CU(ctx, cudaStreamSynchronize(sl.cs));
+        return bytes;
     }
     return (int)sl.out_bytes;
 }

@@ -302,6 +302,45 @@ compact_scatter(const uint8_t *__restrict__ keep, const int16_t *__restrict__ de
 }
 
 // ---------------------------------------------------------------------------
+// Concat of camera payloads whose record counts only exist on the device (-c compaction): what sendStitchToUnity
+// (src/pcs-multicamera-client.cpp:385-395) does with the n_shorts readCloud hands it -- every downsample-th record of
+// every camera in camera order behind the int32 byte count -- with the counts read from device memory.
+struct CountedTable {
+    const int16_t *src[MAX_CAMS];
+    const int32_t *cnt_dev[MAX_CAMS];     // record count on the device, or NULL: cnt_fixed
+    int32_t cnt_fixed[MAX_CAMS];
+    int32_t n_cams, downsample;
+};
+__global__ void __launch_bounds__(256)
+stitch_counted(CountedTable t, uint8_t *__restrict__ stitched, int32_t *__restrict__ total_out) {
+    __shared__ int32_t off[MAX_CAMS + 1];
+    if (threadIdx.x == 0) {
+        int32_t run = 0;
+        for (int c = 0; c < t.n_cams; ++c) {
+            const int32_t n = t.cnt_dev[c] ? *t.cnt_dev[c] : t.cnt_fixed[c];
+            off[c] = run;
+            run += (n + t.downsample - 1) / t.downsample;     // for (j = 0; j < n_shorts; j += 5 * downsample), :388
+        }
+        off[t.n_cams] = run;
+        if (blockIdx.x == 0) {
+            *reinterpret_cast<int32_t *>(stitched) = run * 10;   // :394-395
+            *total_out = run * 10;
+        }
+    }
+    __syncthreads();
+    int16_t *out = reinterpret_cast<int16_t *>(stitched + 4);
+    const int total = off[t.n_cams];
+    int c = 0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+        while (c + 1 < t.n_cams && j >= off[c + 1]) ++c;
+        while (c > 0 && j < off[c]) --c;
+        const int16_t *r = t.src[c] + 5 * (size_t)(j - off[c]) * t.downsample;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) out[5 * (size_t)j + q] = r[q];
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Stitch side.  One table per launch, passed by value (fits the 4 KB parameter bank).
 struct CamTable {
     const int16_t *src[MAX_CAMS];

@@ -542,3 +542,33 @@ def test_voxel_merge_of_a_smooth_scene(R, variant):
             got = c.voxel_merge(rec, leaf)
             assert np.array_equal(got, R.voxel_merge(rec, leaf)), leaf
     c.close()
+
+
+@pytest.mark.parametrize("downsample", [1, 3])
+def test_stitch_frames_with_cutoff_streams(R, downsample):
+    """-c on the camera (src/pcs-camera-optimized.cpp:499-577) + the stitcher's concat: the compacted record counts only exist
+    on the device, the concat reads them there.  One -c camera with the reference's reversed mask lanes, one with straight
+    lanes, one without -c."""
+    w, h = 848, 480
+    c = pcs.Context(device=0, max_streams=3)
+    cal = oracle.make_calib(w, h, translation=synth.D2C_BASELINE)
+    zs, cols, want = [], [], []
+    for cam, (cut, rev) in enumerate([(True, True), (False, True), (True, False)]):
+        d = pcs.stream_desc(w, h, tf=synth.TF_CAMERA, translation=synth.D2C_BASELINE, cutoff=cut, lane_reversed=rev)
+        c.set_stream(cam, d)
+        z, col = synth.depth_frame(w, h, cam, 2, lo=300, hi=2600), synth.color_frame(w, h, cam, 2)
+        zs.append(z)
+        cols.append(col)
+        xyz, uv = R.deproject(cal, z)
+        if cut and rev:
+            rec = R.pack(xyz, uv, col, w, h, 3, w * 3, synth.TF_CAMERA, cutoff=True)
+        else:
+            rec = R.pack(xyz, uv, col, w, h, 3, w * 3, synth.TF_CAMERA)
+            if cut:
+                rec = rec[(xyz[:, 2] > 0) & (xyz[:, 2] <= 1.5) & (xyz[:, 0] > -2) & (xyz[:, 0] <= 2)]
+        want.append(rec.reshape(-1))
+    assert 1000 < want[0].size // 5 < w * h and want[1].size // 5 == w * h
+    for rep in range(2):                      # the slot is reused
+        got = c.stitch_frames([0, 1, 2], zs, cols, downsample)
+        assert np.array_equal(got, R.concat(want, downsample))
+    c.close()
