@@ -42,7 +42,7 @@ extern "C" {
 #define PCS_API
 #endif
 
-#define PCS_B200_ABI_VERSION 1
+#define PCS_B200_ABI_VERSION 2
 #define PCS_B200_RECORD_BYTES 10
 #define PCS_B200_HEADER_BYTES 4
 /* src/pcs-camera-optimized.cpp:27,157,673: short[BUF_SIZE] buffer, memset(BUF_SIZE bytes) */
@@ -60,10 +60,19 @@ typedef enum pcs_status {
     PCS_ERR_CAPACITY = -5     /* output does not fit the buffer given */
 } pcs_status;
 
-/* rs2_intrinsics without the distortion model (D400: all coefficients zero). */
+/* rs2_intrinsics.  model / coeffs follow rs2_distortion: 0 = none (D400 depth: all coefficients zero),
+ * 1 = modified Brown-Conrady (applied when a point is projected: the colour intrinsics),
+ * 2 = inverse Brown-Conrady (applied when a pixel is deprojected: the depth intrinsics); coeffs = k1, k2, p1, p2, k3.
+ * Streams with a distortion model run the general kernel (the arithmetic is oracle/SPEC.md s1's restatement of
+ * librealsense's rsutil.h, parity unpinned like the rest of the deprojection).  A zero-initialised tail means "none". */
+#define PCS_B200_DISTORTION_NONE 0
+#define PCS_B200_DISTORTION_MODIFIED_BROWN_CONRADY 1
+#define PCS_B200_DISTORTION_INVERSE_BROWN_CONRADY 2
 typedef struct pcs_intrinsics {
     int32_t width, height;
     float ppx, ppy, fx, fy;
+    int32_t model;
+    float coeffs[5];
 } pcs_intrinsics;
 
 /* Everything the reference keeps in compile-time constants and globals

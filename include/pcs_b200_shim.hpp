@@ -45,6 +45,25 @@ private:
     pcs_ctx *ctx_ = nullptr;
 };
 
+// rs2_intrinsics -> pcs_intrinsics, distortion included (templated so that this header does not need librealsense2:
+// any struct with rs2_intrinsics' members works).  librealsense's rs2_distortion numbers NONE = 0, MODIFIED_BROWN_CONRADY
+// = 1, INVERSE_BROWN_CONRADY = 2 -- the values of PCS_B200_DISTORTION_*; BROWN_CONRADY (4: the image is already
+// rectified, rsutil.h applies nothing) maps to none, the fisheye models pass through and pcs_b200_set_stream refuses them.
+template <class Rs2Intrinsics>
+inline pcs_intrinsics intrinsics_from_rs2(const Rs2Intrinsics &in) {
+    pcs_intrinsics o;
+    std::memset(&o, 0, sizeof o);
+    o.width = in.width; o.height = in.height;
+    o.ppx = in.ppx; o.ppy = in.ppy; o.fx = in.fx; o.fy = in.fy;
+    const int model = (int)in.model;
+    bool any = false;
+    for (int i = 0; i < 5; ++i) any = any || in.coeffs[i] != 0.f;
+    o.model = (model == 4 || !any) ? PCS_B200_DISTORTION_NONE : model;
+    if (o.model != PCS_B200_DISTORTION_NONE)
+        for (int i = 0; i < 5; ++i) o.coeffs[i] = in.coeffs[i];
+    return o;
+}
+
 // A stream descriptor with the reference's constants filled in: tf_mat
 // (src/pcs-camera-optimized.cpp:64-67 layout: row-major 4x4) and the -c bounds (:398-401).
 inline pcs_stream_desc make_stream_desc(const pcs_intrinsics &depth, const pcs_intrinsics &color,

@@ -30,7 +30,7 @@ REF = os.path.join(HERE, "_ref")
 
 class Intrinsics(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("ppx", C.c_float), ("ppy", C.c_float),
-                ("fx", C.c_float), ("fy", C.c_float)]
+                ("fx", C.c_float), ("fy", C.c_float), ("model", C.c_int), ("coeffs", C.c_float * 5)]
 
 
 class Calib(C.Structure):
@@ -45,7 +45,7 @@ assert PCLPOINT.itemsize == 32
 
 def make_calib(dw, dh, cw=None, ch=None, dfx=None, dfy=None, dppx=None, dppy=None, cfx=None,
                cfy=None, cppx=None, cppy=None, rotation=None, translation=(0.0, 0.0, 0.0),
-               depth_scale=0.001):
+               depth_scale=0.001, depth_distortion=None, color_distortion=None):
     """Calibration with the SURVEY s8(d) defaults: f = W/2, pp = ((W-1)/2, (H-1)/2)."""
     cw = dw if cw is None else cw
     ch = dh if ch is None else ch
@@ -56,6 +56,10 @@ def make_calib(dw, dh, cw=None, ch=None, dfx=None, dfy=None, dppx=None, dppy=Non
     c.color = Intrinsics(cw, ch, (cw - 1) / 2 if cppx is None else cppx,
                          (ch - 1) / 2 if cppy is None else cppy, cw / 2 if cfx is None else cfx,
                          cw / 2 if cfy is None else cfy)
+    if depth_distortion is not None:          # inverse Brown-Conrady (k1, k2, p1, p2, k3), applied on deprojection
+        c.depth.model, c.depth.coeffs = 2, (C.c_float * 5)(*depth_distortion)
+    if color_distortion is not None:          # modified Brown-Conrady, applied on projection
+        c.color.model, c.color.coeffs = 1, (C.c_float * 5)(*color_distortion)
     rot = (1, 0, 0, 0, 1, 0, 0, 0, 1) if rotation is None else tuple(rotation)
     c.rotation = (C.c_float * 9)(*rot)
     c.translation = (C.c_float * 3)(*translation)

@@ -29,6 +29,37 @@ static int imax(int a, int b) { return a > b ? a : b; }
  * rsutil.h rs2_deproject_pixel_to_point / rs2_transform_point_to_point /
  * rs2_project_point_to_pixel with zero distortion, and proc/pointcloud.cpp's
  * tex = pixel / (width, height), z == 0 -> tex (0,0).  PARITY UNPINNED. */
+/* librealsense2 rsutil.h (2.16): the radial factor and the two Brown-Conrady forms, written as that header writes
+ * them (this file is compiled with -ffp-contract=off, so every operator below rounds once, left to right). */
+static float bc_radial(const float *k, float r2)
+{
+    return 1 + k[0] * r2 + k[1] * r2 * r2 + k[4] * r2 * r2 * r2;
+}
+/* rs2_project_point_to_pixel, RS2_DISTORTION_MODIFIED_BROWN_CONRADY */
+static void bc_project(const float *k, float *x, float *y)
+{
+    const float r2 = *x * *x + *y * *y;
+    const float f = bc_radial(k, r2);
+    *x *= f;
+    *y *= f;
+    {
+        const float dx = *x + 2 * k[2] * *x * *y + k[3] * (r2 + 2 * *x * *x);
+        const float dy = *y + 2 * k[3] * *x * *y + k[2] * (r2 + 2 * *y * *y);
+        *x = dx;
+        *y = dy;
+    }
+}
+/* rs2_deproject_pixel_to_point, RS2_DISTORTION_INVERSE_BROWN_CONRADY */
+static void bc_deproject(const float *k, float *x, float *y)
+{
+    const float r2 = *x * *x + *y * *y;
+    const float f = bc_radial(k, r2);
+    const float ux = *x * f + 2 * k[2] * *x * *y + k[3] * (r2 + 2 * *x * *x);
+    const float uy = *y * f + 2 * k[3] * *x * *y + k[2] * (r2 + 2 * *y * *y);
+    *x = ux;
+    *y = uy;
+}
+
 void pcs_oracle_deproject(const pcs_oracle_calib *c, const uint16_t *z16, float *xyz, float *uv,
                           int num_threads)
 {
@@ -41,8 +72,9 @@ void pcs_oracle_deproject(const pcs_oracle_calib *c, const uint16_t *z16, float 
         for (int x = 0; x < W; ++x) {
             const size_t i = (size_t)y * W + x;
             const float depth = c->depth_scale * (float)z16[i];
-            const float nx = ((float)x - c->depth.ppx) / c->depth.fx;
-            const float ny = ((float)y - c->depth.ppy) / c->depth.fy;
+            float nx = ((float)x - c->depth.ppx) / c->depth.fx;
+            float ny = ((float)y - c->depth.ppy) / c->depth.fy;
+            if (c->depth.model == 2) bc_deproject(c->depth.coeffs, &nx, &ny);
             const float p0 = depth * nx, p1 = depth * ny, p2 = depth;
             xyz[3 * i + 0] = p0;
             xyz[3 * i + 1] = p1;
@@ -51,8 +83,10 @@ void pcs_oracle_deproject(const pcs_oracle_calib *c, const uint16_t *z16, float 
                 const float t0 = R[0] * p0 + R[3] * p1 + R[6] * p2 + T[0];
                 const float t1 = R[1] * p0 + R[4] * p1 + R[7] * p2 + T[1];
                 const float t2 = R[2] * p0 + R[5] * p1 + R[8] * p2 + T[2];
-                const float px = (t0 / t2) * c->color.fx + c->color.ppx;
-                const float py = (t1 / t2) * c->color.fy + c->color.ppy;
+                float qx = t0 / t2, qy = t1 / t2;
+                if (c->color.model == 1) bc_project(c->color.coeffs, &qx, &qy);
+                const float px = qx * c->color.fx + c->color.ppx;
+                const float py = qy * c->color.fy + c->color.ppy;
                 uv[2 * i + 0] = px / cw;
                 uv[2 * i + 1] = py / chh;
             } else {

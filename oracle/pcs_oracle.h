@@ -26,9 +26,13 @@
 extern "C" {
 #endif
 
+/* model / coeffs: rs2_distortion (0 none, 1 modified Brown-Conrady: applied when projecting into this sensor,
+ * 2 inverse Brown-Conrady: applied when deprojecting from it); coeffs = k1, k2, p1, p2, k3. */
 typedef struct pcs_oracle_intrinsics {
     int width, height;
     float ppx, ppy, fx, fy;
+    int model;
+    float coeffs[5];
 } pcs_oracle_intrinsics;
 
 /* depth -> colour calibration, rs2_intrinsics / rs2_extrinsics conventions:

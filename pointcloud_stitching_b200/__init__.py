@@ -40,7 +40,7 @@ class PcsError(RuntimeError):
 
 class Intrinsics(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("ppx", C.c_float), ("ppy", C.c_float),
-                ("fx", C.c_float), ("fy", C.c_float)]
+                ("fx", C.c_float), ("fy", C.c_float), ("model", C.c_int32), ("coeffs", C.c_float * 5)]
 
 
 class StreamDesc(C.Structure):
@@ -73,7 +73,8 @@ class FrameJob(C.Structure):
 
 def stream_desc(dw, dh, cw=None, ch=None, tf=None, translation=(0.0, 0.0, 0.0), rotation=None,
                 depth_scale=0.001, bpp=3, stride=None, cutoff=False, lane_reversed=True,
-                dfx=None, dfy=None, dppx=None, dppy=None, cfx=None, cfy=None, cppx=None, cppy=None):
+                dfx=None, dfy=None, dppx=None, dppy=None, cfx=None, cfy=None, cppx=None, cppy=None,
+                depth_distortion=None, color_distortion=None):
     """A pcs_stream_desc with the SURVEY s8(d) synthetic calibration as defaults
     (f = W/2, principal point at the image centre, RGB8 colour of the depth size)."""
     cw = dw if cw is None else cw
@@ -85,6 +86,10 @@ def stream_desc(dw, dh, cw=None, ch=None, tf=None, translation=(0.0, 0.0, 0.0), 
     d.color = Intrinsics(cw, ch, (cw - 1) / 2 if cppx is None else cppx,
                          (ch - 1) / 2 if cppy is None else cppy, cw / 2 if cfx is None else cfx,
                          cw / 2 if cfy is None else cfy)
+    if depth_distortion is not None:      # rs2 inverse Brown-Conrady: k1, k2, p1, p2, k3
+        d.depth.model, d.depth.coeffs = 2, (C.c_float * 5)(*depth_distortion)
+    if color_distortion is not None:      # rs2 modified Brown-Conrady
+        d.color.model, d.color.coeffs = 1, (C.c_float * 5)(*color_distortion)
     d.d2c_rotation = (C.c_float * 9)(*((1, 0, 0, 0, 1, 0, 0, 0, 1) if rotation is None else rotation))
     d.d2c_translation = (C.c_float * 3)(*translation)
     d.depth_scale = depth_scale

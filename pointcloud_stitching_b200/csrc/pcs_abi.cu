@@ -180,6 +180,7 @@ bool is_identity3(const float *r) {
 
 // Choose the cheapest tex-coordinate path that is still bit-exact (pcs_device.cuh).
 int pick_tex_mode(const pcs_stream_desc &d) {
+    if (d.depth.model != PCS_B200_DISTORTION_NONE || d.color.model != PCS_B200_DISTORTION_NONE) return TEX_GENERAL;
     if (!is_identity3(d.d2c_rotation)) return TEX_GENERAL;
     const bool t0 = d.d2c_translation[0] == 0.f && d.d2c_translation[1] == 0.f &&
                     d.d2c_translation[2] == 0.f;
@@ -234,6 +235,9 @@ void digest(const pcs_stream_desc &d, StreamParams &p) {
     memcpy(p.R, d.d2c_rotation, sizeof p.R);
     memcpy(p.T, d.d2c_translation, sizeof p.T);
     memcpy(p.tf, d.tf, sizeof p.tf);
+    p.dmodel = d.depth.model; p.cmodel = d.color.model;
+    memcpy(p.dcoef, d.depth.coeffs, sizeof p.dcoef);
+    memcpy(p.ccoef, d.color.coeffs, sizeof p.ccoef);
     p.cutoff = d.cutoff != 0; p.lane_rev = d.cutoff_lane_reversed != 0;
     p.z_lo = d.z_lo; p.z_hi = d.z_hi; p.x_lo = d.x_lo; p.x_hi = d.x_hi;
 }
@@ -444,6 +448,10 @@ int pcs_b200_set_stream(pcs_ctx *ctx, int stream, const pcs_stream_desc *desc) {
     if (d.depth.width < 0 || d.depth.height < 0 ||
         (long long)d.depth.width * d.depth.height > (1ll << 28))
         return fail(ctx, PCS_ERR_INVALID, "bad depth geometry");
+    // librealsense applies inverse Brown-Conrady when deprojecting and modified Brown-Conrady when projecting
+    if ((d.depth.model != PCS_B200_DISTORTION_NONE && d.depth.model != PCS_B200_DISTORTION_INVERSE_BROWN_CONRADY) ||
+        (d.color.model != PCS_B200_DISTORTION_NONE && d.color.model != PCS_B200_DISTORTION_MODIFIED_BROWN_CONRADY))
+        return fail(ctx, PCS_ERR_UNSUPPORTED, "distortion models: depth none / inverse Brown-Conrady, colour none / modified Brown-Conrady");
     DeviceGuard dg_(ctx->device);
     StreamState &s = ctx->streams[stream];
     std::lock_guard<std::mutex> lk(s.mu);

@@ -36,7 +36,46 @@ struct StreamParams {
     // row taps (device memory, H entries), proven on the host to be what the exact chain yields for every depth
     // value (pcs_abi.cu make_rowmap); NULL when the tap row is the pixel's own row
     const int32_t *rowmap;
+    // lens distortion (rs2_distortion: 0 none, 1 modified Brown-Conrady on projection, 2 inverse Brown-Conrady on
+    // deprojection); coefficients k1, k2, p1, p2, k3.  Any model forces TEX_GENERAL.
+    int dmodel, cmodel;
+    float dcoef[5], ccoef[5];
 };
+
+// librealsense rsutil.h, evaluated left to right without contraction (oracle/SPEC.md s1):
+//   r2 = x*x + y*y;  f = 1 + k1*r2 + k2*r2*r2 + k3*r2*r2*r2
+__device__ __forceinline__ float bc_radial(const float *c, float r2) {
+    float f = __fadd_rn(1.0f, __fmul_rn(c[0], r2));
+    f = __fadd_rn(f, __fmul_rn(__fmul_rn(c[1], r2), r2));
+    f = __fadd_rn(f, __fmul_rn(__fmul_rn(__fmul_rn(c[4], r2), r2), r2));
+    return f;
+}
+// rs2_project_point_to_pixel, RS2_DISTORTION_MODIFIED_BROWN_CONRADY:
+//   x *= f; y *= f; dx = x + 2*p1*x*y + p2*(r2 + 2*x*x); dy = y + 2*p2*x*y + p1*(r2 + 2*y*y)
+__device__ __forceinline__ void bc_project(const float *c, float &x, float &y) {
+    const float r2 = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+    const float f = bc_radial(c, r2);
+    x = __fmul_rn(x, f);
+    y = __fmul_rn(y, f);
+    const float dx = __fadd_rn(__fadd_rn(x, __fmul_rn(__fmul_rn(__fmul_rn(2.0f, c[2]), x), y)),
+                               __fmul_rn(c[3], __fadd_rn(r2, __fmul_rn(__fmul_rn(2.0f, x), x))));
+    const float dy = __fadd_rn(__fadd_rn(y, __fmul_rn(__fmul_rn(__fmul_rn(2.0f, c[3]), x), y)),
+                               __fmul_rn(c[2], __fadd_rn(r2, __fmul_rn(__fmul_rn(2.0f, y), y))));
+    x = dx;
+    y = dy;
+}
+// rs2_deproject_pixel_to_point, RS2_DISTORTION_INVERSE_BROWN_CONRADY:
+//   ux = x*f + 2*p1*x*y + p2*(r2 + 2*x*x); uy = y*f + 2*p2*x*y + p1*(r2 + 2*y*y)
+__device__ __forceinline__ void bc_deproject(const float *c, float &x, float &y) {
+    const float r2 = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+    const float f = bc_radial(c, r2);
+    const float ux = __fadd_rn(__fadd_rn(__fmul_rn(x, f), __fmul_rn(__fmul_rn(__fmul_rn(2.0f, c[2]), x), y)),
+                               __fmul_rn(c[3], __fadd_rn(r2, __fmul_rn(__fmul_rn(2.0f, x), x))));
+    const float uy = __fadd_rn(__fadd_rn(__fmul_rn(y, f), __fmul_rn(__fmul_rn(__fmul_rn(2.0f, c[3]), x), y)),
+                               __fmul_rn(c[2], __fadd_rn(r2, __fmul_rn(__fmul_rn(2.0f, y), y))));
+    x = ux;
+    y = uy;
+}
 
 // x86 CVTTSS2SI semantics: truncate; NaN / out of range -> 0x80000000.
 // (CUDA's cvt.rzi saturates +overflow to INT_MAX and maps NaN to 0 instead.)
@@ -81,6 +120,7 @@ __device__ __forceinline__ void deproject_tap(const StreamParams &s, uint32_t z1
                                               float nx, float ny, float &p0, float &p1, float &p2,
                                               int &xi, int &yi) {
     const float depth = __fmul_rn(s.depth_scale, (float)z16);
+    if (MODE == TEX_GENERAL && s.dmodel == 2) bc_deproject(s.dcoef, nx, ny);
     p0 = __fmul_rn(depth, nx);
     p1 = __fmul_rn(depth, ny);
     p2 = depth;
@@ -120,8 +160,10 @@ __device__ __forceinline__ void deproject_tap(const StreamParams &s, uint32_t z1
             t2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s.R[2], p0), __fmul_rn(s.R[5], p1)),
                                      __fmul_rn(s.R[8], p2)), s.T[2]);
         }
-        const float px = __fadd_rn(__fmul_rn(__fdiv_rn(t0, t2), s.cfx), s.cppx);
-        const float py = __fadd_rn(__fmul_rn(__fdiv_rn(t1, t2), s.cfy), s.cppy);
+        float qx = __fdiv_rn(t0, t2), qy = __fdiv_rn(t1, t2);
+        if (MODE == TEX_GENERAL && s.cmodel == 1) bc_project(s.ccoef, qx, qy);
+        const float px = __fadd_rn(__fmul_rn(qx, s.cfx), s.cppx);
+        const float py = __fadd_rn(__fmul_rn(qy, s.cfy), s.cppy);
         u = __fdiv_rn(px, s.cwf);
         v = __fdiv_rn(py, s.chf);
     }

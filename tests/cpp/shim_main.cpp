@@ -37,7 +37,15 @@ int main() {
     cal.translation[0] = 0.015f;
     cal.depth_scale = 0.001f;
 
-    pcs_intrinsics di = {W, H, 639.5f, 359.5f, 640.f, 640.f};
+    // what rs2::video_stream_profile::get_intrinsics() hands back (rs2_intrinsics' members); a Brown-Conrady model
+    // with all-zero coefficients (every D400 depth stream) must come out as "none" and keep the fast kernels
+    struct { int width, height; float ppx, ppy, fx, fy; int model; float coeffs[5]; } rs = {
+        W, H, 639.5f, 359.5f, 640.f, 640.f, 4, {0.f, 0.f, 0.f, 0.f, 0.f}};
+    pcs_intrinsics di = pcs_b200::intrinsics_from_rs2(rs);
+    if (di.model != PCS_B200_DISTORTION_NONE || di.fx != 640.f || di.width != W) { std::printf("intrinsics_from_rs2 broken\n"); return 1; }
+    rs.model = 1; rs.coeffs[0] = 0.1f;
+    if (pcs_b200::intrinsics_from_rs2(rs).model != PCS_B200_DISTORTION_MODIFIED_BROWN_CONRADY ||
+        pcs_b200::intrinsics_from_rs2(rs).coeffs[0] != 0.1f) { std::printf("intrinsics_from_rs2 drops the model\n"); return 1; }
     int failures = 0;
     try {
         pcs_b200::Context ctx(2);

@@ -30,18 +30,29 @@ def test_header_symbols_exported():
 
 
 def test_abi_version_and_status_strings():
-    assert pcs.lib.pcs_b200_abi_version() == 1
+    assert pcs.lib.pcs_b200_abi_version() == 2
     assert pcs.lib.pcs_b200_status_string(0) == b"ok"
     assert pcs.lib.pcs_b200_status_string(pcs.PCS_ERR_CUDA) == b"CUDA error"
     assert pcs.lib.pcs_b200_status_string(123) == b"ok"          # counts / byte sizes are successes
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
     # sizes the C side was compiled with (include/pcs_b200.h)
-    assert C.sizeof(pcs.Intrinsics) == 24
-    assert C.sizeof(pcs.StreamDesc) == 2 * 24 + 9 * 4 + 3 * 4 + 4 + 4 + 4 + 16 * 4 + 4 + 4 * 4 + 4
+    assert C.sizeof(pcs.Intrinsics) == 48
+    assert C.sizeof(pcs.StreamDesc) == 2 * 48 + 9 * 4 + 3 * 4 + 4 + 4 + 4 + 16 * 4 + 4 + 4 * 4 + 4
     assert C.sizeof(pcs.Config) == 16
     assert C.sizeof(pcs.FrameJob) == 8 + 5 * 8
+    # and what a C compiler makes of the header itself
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "pcs_b200.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(pcs_intrinsics), sizeof(pcs_stream_desc), sizeof(pcs_config), sizeof(pcs_frame_job), '
+                   'sizeof(pcs_ipc_handle), sizeof(pcs_shard_peers)); return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-I" + os.path.join(pcs.ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True, text=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [C.sizeof(pcs.Intrinsics), C.sizeof(pcs.StreamDesc), C.sizeof(pcs.Config), C.sizeof(pcs.FrameJob),
+                   C.sizeof(pcs.IpcHandle), C.sizeof(pcs.ShardPeers)]
 
 
 def test_library_contains_sm100a_code_only():

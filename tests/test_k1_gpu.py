@@ -94,6 +94,15 @@ CASES = {
     "480p_aligned": dict(w=848, h=480),
     "480p_baseline": dict(w=848, h=480, translation=synth.D2C_BASELINE),
     "720p_color1080p": dict(w=1280, h=720, cw=1920, ch=1080, translation=synth.D2C_BASELINE),
+    # lens distortion (rs2_intrinsics.model / coeffs): modified Brown-Conrady on the colour sensor, inverse Brown-Conrady
+    # on the depth sensor, both at once with a rotated extrinsic and colour of another size
+    "480p_color_distortion": dict(w=848, h=480, translation=synth.D2C_BASELINE,
+                                  color_distortion=(0.12, -0.25, 0.0012, -0.0008, 0.09)),
+    "480p_depth_distortion": dict(w=848, h=480, depth_distortion=(-0.05, 0.07, 0.0005, 0.0011, -0.02)),
+    "720p_both_distortions_rot_1080p": dict(w=1280, h=720, cw=1920, ch=1080, translation=(0.015, 0.001, -0.002),
+                                            rotation=small_rotation(0.004, -0.003, 0.005),
+                                            depth_distortion=(0.02, -0.03, 0.0004, -0.0006, 0.01),
+                                            color_distortion=(0.1, -0.21, 0.001, 0.0015, 0.07)),
     "720p_rgba_padded": dict(w=1280, h=720, bpp=4, stride=1280 * 4 + 64, translation=synth.D2C_BASELINE),
     "odd_intrinsics": dict(w=640, h=360, translation=(0.02, 0.01, -0.005), dfx=381.7, dfy=380.9,
                            dppx=322.3, dppy=178.8, cfx=610.2, cfy=611.9, cppx=318.4, cppy=182.1),
@@ -348,6 +357,17 @@ def test_error_paths(ctx0):
         ctx0.set_stream(99, pcs.stream_desc(8, 1))
     with pytest.raises(pcs.PcsError):
         ctx0.set_stream(0, pcs.stream_desc(8, 1, bpp=2))
+    # rs2_distortion models librealsense does not apply on this side of the chain are refused, not ignored
+    bad = pcs.stream_desc(64, 4, color_distortion=(0.1, 0, 0, 0, 0))
+    bad.color.model = 3                                           # F-Theta
+    with pytest.raises(pcs.PcsError) as e:
+        ctx0.set_stream(5, bad)
+    assert e.value.status == pcs.PCS_ERR_UNSUPPORTED
+    bad = pcs.stream_desc(64, 4, depth_distortion=(0.1, 0, 0, 0, 0))
+    bad.depth.model = 1                                           # modified Brown-Conrady belongs to projection
+    with pytest.raises(pcs.PcsError) as e:
+        ctx0.set_stream(5, bad)
+    assert e.value.status == pcs.PCS_ERR_UNSUPPORTED
     ctx0.set_stream(5, pcs.stream_desc(1284, 4))                  # width % 8 != 0
     with pytest.raises(pcs.PcsError) as e:
         ctx0.send_xyzrgb(5, np.zeros(1284 * 4, np.uint16), np.zeros(1284 * 4 * 3, np.uint8))

@@ -153,6 +153,88 @@ def test_deproject_spec_properties(restatement):
     assert xyz.tobytes() == xyz2.tobytes()
 
 
+def _np_deproject(cal, z16):
+    """oracle/SPEC.md s1 written again in numpy float32 (every operator rounds once): an independent reading of the
+    same text, distortion included."""
+    f = np.float32
+    W, H = cal.depth.width, cal.depth.height
+    x, y = np.meshgrid(np.arange(W, dtype=f), np.arange(H, dtype=f))
+    nx, ny = (x - f(cal.depth.ppx)) / f(cal.depth.fx), (y - f(cal.depth.ppy)) / f(cal.depth.fy)
+
+    def radial(k, r2):
+        return f(1) + k[0] * r2 + k[1] * r2 * r2 + k[4] * r2 * r2 * r2
+
+    if cal.depth.model == 2:
+        k = [f(v) for v in cal.depth.coeffs]
+        r2 = nx * nx + ny * ny
+        fr = radial(k, r2)
+        ux = nx * fr + f(2) * k[2] * nx * ny + k[3] * (r2 + f(2) * nx * nx)
+        uy = ny * fr + f(2) * k[3] * nx * ny + k[2] * (r2 + f(2) * ny * ny)
+        nx, ny = ux, uy
+    depth = f(cal.depth_scale) * z16.reshape(H, W).astype(f)
+    p0, p1, p2 = depth * nx, depth * ny, depth
+    R, T = [f(v) for v in cal.rotation], [f(v) for v in cal.translation]
+    with np.errstate(all="ignore"):
+        t0 = R[0] * p0 + R[3] * p1 + R[6] * p2 + T[0]
+        t1 = R[1] * p0 + R[4] * p1 + R[7] * p2 + T[1]
+        t2 = R[2] * p0 + R[5] * p1 + R[8] * p2 + T[2]
+        qx, qy = t0 / t2, t1 / t2
+        if cal.color.model == 1:
+            k = [f(v) for v in cal.color.coeffs]
+            r2 = qx * qx + qy * qy
+            fr = radial(k, r2)
+            qx, qy = qx * fr, qy * fr
+            dx = qx + f(2) * k[2] * qx * qy + k[3] * (r2 + f(2) * qx * qx)
+            dy = qy + f(2) * k[3] * qx * qy + k[2] * (r2 + f(2) * qy * qy)
+            qx, qy = dx, dy
+        u = (qx * f(cal.color.fx) + f(cal.color.ppx)) / f(cal.color.width)
+        v = (qy * f(cal.color.fy) + f(cal.color.ppy)) / f(cal.color.height)
+    hole = p2 == 0
+    u[hole], v[hole] = 0, 0
+    return np.stack([p0, p1, p2], -1).reshape(-1, 3), np.stack([u, v], -1).reshape(-1, 2)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(),
+    dict(translation=synth.D2C_BASELINE, color_distortion=(0.12, -0.25, 0.0012, -0.0008, 0.09)),
+    dict(depth_distortion=(-0.05, 0.07, 0.0005, 0.0011, -0.02)),
+    dict(cw=480, ch=270, translation=(0.015, 0.001, -0.002),
+         rotation=(0.99998, 0.005, 0.003, -0.005, 0.99998, -0.004, -0.003, 0.004, 0.99998),
+         depth_distortion=(0.02, -0.03, 0.0004, -0.0006, 0.01), color_distortion=(0.1, -0.21, 0.001, 0.0015, 0.07)),
+])
+def test_deproject_distortion_against_a_second_reading_of_the_spec(restatement, kw):
+    import oracle
+    w, h = 320, 180
+    cal = oracle.make_calib(w, h, **kw)
+    z = synth.depth_frame(w, h, 3, 2)
+    xyz, uv = restatement.deproject(cal, z)
+    xyz2, uv2 = _np_deproject(cal, z)
+    assert xyz.tobytes() == xyz2.tobytes() and uv.tobytes() == uv2.tobytes()
+
+
+def test_deproject_distortion_properties(restatement):
+    import oracle
+    w, h = 320, 180
+    z = synth.depth_frame(w, h, 3, 2)
+    plain = restatement.deproject(oracle.make_calib(w, h, translation=synth.D2C_BASELINE), z)
+    # all-zero coefficients: the radial factor is exactly 1 and the tangential terms exactly 0
+    zero = restatement.deproject(oracle.make_calib(w, h, translation=synth.D2C_BASELINE, depth_distortion=(0,) * 5,
+                                                   color_distortion=(0,) * 5), z)
+    assert np.array_equal(plain[0], zero[0]) and np.array_equal(plain[1], zero[1])
+    # a barrel colour lens pulls taps towards the principal point, more so far from it; the vertices do not move
+    bar = restatement.deproject(oracle.make_calib(w, h, translation=synth.D2C_BASELINE,
+                                                  color_distortion=(-0.2, 0, 0, 0, 0)), z)
+    assert plain[0].tobytes() == bar[0].tobytes()
+    valid = z.reshape(-1) != 0
+    c = np.array([(w - 1) / 2 / w, (h - 1) / 2 / h], np.float32)
+    r_plain = np.linalg.norm((plain[1] - c) * (w, h), axis=1)[valid]
+    r_bar = np.linalg.norm((bar[1] - c) * (w, h), axis=1)[valid]
+    far = r_plain > 20
+    assert np.all(r_bar[far] < r_plain[far])
+    shrink = 1 - r_bar[far] / r_plain[far]
+    assert np.corrcoef(shrink, r_plain[far] ** 2)[0, 1] > 0.99
+
+
 def test_voxel_merge_spec(restatement):
     rec = np.array([[5, 5, 5, 0x0201, 3], [9, 0, 1, 0x0403, 6], [10, 0, 0, 0x1010, 0x10],
                     [-1, -10, -11, 0xFF, 0xFF], [-10, -1, -20, 0x01, 0x01]], np.int16)
