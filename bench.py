@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- Mpoints/s stitched on synthetic 1280x720 depth+RGB streams.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--tex baseline|aligned|rotated|color1080p]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--tex baseline|aligned|rotated|color1080p|rotated1080p]
 
 Headline ("value"): one "step" = one pass of the hot path (depth deprojection + 4x4 transform + colour
 attach + int16 pack, fused kernel K1) over one batch of STREAMS x FRAMES synthetic frames per GPU
@@ -40,7 +40,7 @@ NPTS = W * H
 ALG_BYTES_PER_POINT = 15          # 2 (z16) + 3 (RGB8) + 10 (record), SURVEY s8(d)
 METRIC = "Mpoints/sec stitched (1280x720xN cams)"
 LEAF_MM = 10
-TEX_CHOICES = ["baseline", "aligned", "rotated", "color1080p"]
+TEX_CHOICES = ["baseline", "aligned", "rotated", "color1080p", "rotated1080p"]
 
 
 def parse():
@@ -150,12 +150,15 @@ def tex_calibration(tex):
         cal["rotation"] = synth.D2C_ROTATION_SMALL
     elif tex == "color1080p":
         cal["cw"], cal["ch"] = 1920, 1080
+    elif tex == "rotated1080p":      # the reference's recording geometry (src/pcs-camera-grab-frames.cpp:69-70) on a real D4xx
+        cal["cw"], cal["ch"], cal["rotation"] = 1920, 1080, synth.D2C_ROTATION_SMALL
     return cal
 
 
 def tex_label(tex):
     return {"baseline": "15 mm baseline", "aligned": "identity", "rotated": "15 mm baseline + 0.3 deg rotation",
-            "color1080p": "15 mm baseline, 1920x1080 colour"}[tex]
+            "color1080p": "15 mm baseline, 1920x1080 colour",
+            "rotated1080p": "15 mm baseline + 0.3 deg rotation, 1920x1080 colour"}[tex]
 
 
 def headline_config(args, world):
@@ -692,7 +695,7 @@ def main():
     # colour bytes per depth pixel: the rows the taps can land in.  Same-size frames: every row, 3 B/px.  A colour frame
     # of another size behind a pure x baseline: depth row y taps colour row floor((y - ppy) / fy * cfy + cppy + .5) whatever
     # the depth (the library proves it per stream and reads only those rows), so the rows in between are never needed
-    if args.tex == "color1080p":
+    if args.tex in ("color1080p", "rotated1080p"):      # (rotated: the same count of rows, sheared along x)
         tapped = len({int(np.floor((y - (H - 1) / 2) / (W / 2) * (cw / 2) + (ch - 1) / 2 + 0.5)) for y in range(H)})
     else:
         tapped = ch

@@ -742,10 +742,6 @@ static int batch_create_impl(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs
             const StreamParams &p = ctx->streams[b->jobs[i].stream].params;
             ok = ok && pipe_supports(p) && !b->jobs[i].xyzrgb &&
                  !(reinterpret_cast<uintptr_t>(b->jobs[i].payload) & 15);
-            // a rotated calibration is instruction-bound either way and the windowed pipeline
-            // measured no faster than the direct kernel for it (profiles/r01_k1_geometries.md):
-            // auto mode keeps the simpler kernel, kernel_variant = 2 (or a fan-out) forces the pipeline
-            if (p.tex_mode == TEX_GENERAL && ctx->kernel_variant == 0 && !n_peers) ok = false;
         }
         if (ok) {
             std::vector<StreamParams> sp(ctx->max_streams);
@@ -889,7 +885,8 @@ int pcs_b200_batch_run(pcs_ctx *ctx, pcs_batch *b, void *cuda_stream) {
                         "stream %d was reconfigured after this batch was created (only tf may change under a live "
                         "batch): destroy the batch and create it again", sg.first);
     if (b->use_pipe) {
-        pipe_launch(b->pipe, b->d_jobs, ctx->d_params, cs);
+        pipe_launch(b->pipe, b->d_jobs, ctx->d_params, cs,
+                    [](void *c, int stream) -> const float * { return static_cast<pcs_ctx *>(c)->streams[stream].params.tf; }, ctx);
         CU(ctx, cudaGetLastError());
         return PCS_OK;
     }

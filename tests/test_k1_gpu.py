@@ -174,15 +174,27 @@ def test_extreme_depths(ctx, R):
         assert np.array_equal(rec, R.frame(cal, z, col, 3, w * 3, synth.TF_STITCH[7]))
 
 
-@pytest.mark.parametrize("w,h", [(1280, 720), (848, 480)])
-def test_every_depth_value_at_every_column(ctx, R, w, h):
+SWEEPS = {
+    "baseline": dict(translation=synth.D2C_BASELINE),
+    # guarded taps (pcs_guard.h): every depth value meets the guard at every column, with the near depths the guard
+    # hands to the exact chain, the taps that leave the staged window and the ones clamped at the frame's border
+    "rotated": dict(translation=synth.D2C_BASELINE, rotation=synth.D2C_ROTATION_SMALL),
+    "rotated_1080p": dict(cw=1920, ch=1080, translation=(0.0149, 0.0003, -0.0004), rotation=small_rotation(-0.003, 0.004, -0.006)),
+}
+
+
+@pytest.mark.parametrize("w,h,sweep", [(1280, 720, "baseline"), (848, 480, "baseline"), (1280, 720, "rotated"),
+                                       (848, 480, "rotated"), (1280, 720, "rotated_1080p")])
+def test_every_depth_value_at_every_column(ctx, R, w, h, sweep):
     """Exhaustive over the kernel's data-dependent arithmetic: every z16 in 0..65535 at every
-    column (rows of constant depth), 15 mm baseline, so that every (t0 / depth, px / width)
-    division the tap chain can meet at this geometry is compared with the oracle."""
-    cal, desc = calib_and_desc(w, h, tf=synth.TF_STITCH[5], translation=synth.D2C_BASELINE)
+    column (rows of constant depth), so that every (t0 / depth, px / width) division -- or, under a rotated
+    calibration, every guard decision -- the tap chain can meet at this geometry is compared with the oracle."""
+    kw = dict(SWEEPS[sweep])
+    cw, ch = kw.pop("cw", w), kw.pop("ch", h)
+    cal, desc = calib_and_desc(w, h, cw, ch, tf=synth.TF_STITCH[5], **kw)
     ctx.set_stream(0, desc)
     n_frames = -(-65536 // h)
-    col = synth.color_frame(w, h, 11, 0)
+    col = synth.color_frame(cw, ch, 11, 0)
     jobs = []
     for f in range(n_frames):
         z = ((np.arange(h, dtype=np.int64) + f * h) % 65536).astype(np.uint16)
@@ -191,7 +203,7 @@ def test_every_depth_value_at_every_column(ctx, R, w, h):
         chunk = jobs[lo:lo + 32]
         got = run_batch(ctx, chunk, None)
         for (_, z, c), (rec, _, _) in zip(chunk, got):
-            want = R.frame(cal, z, c, 3, w * 3, synth.TF_STITCH[5])
+            want = R.frame(cal, z, c, 3, cw * 3, synth.TF_STITCH[5])
             bad = np.nonzero((rec != want).any(axis=1))[0]
             assert bad.size == 0, "z16=%d x=%d: got %s want %s" % (
                 z.reshape(-1)[bad[0]], bad[0] % w, rec[bad[0]], want[bad[0]])
