@@ -115,8 +115,9 @@ __device__ __forceinline__ uint32_t load_rgb(const uint8_t *__restrict__ base, i
 // oracle/SPEC.md s1 for one pixel: vertex p and the colour tap (xi, yi).
 // nx, ny are ((x - ppx) / fx, (y - ppy) / fy), computed by the caller (they are
 // shared along rows / columns).
-template <int MODE>
-__device__ __forceinline__ void deproject_tap(const StreamParams &s, uint32_t z16, int x, int y,
+// S: StreamParams, or any struct with its calibration members (the pipelined kernel passes its parameter-bank copy).
+template <int MODE, class S>
+__device__ __forceinline__ void deproject_tap(const S &s, uint32_t z16, int x, int y,
                                               float nx, float ny, float &p0, float &p1, float &p2,
                                               int &xi, int &yi) {
     const float depth = __fmul_rn(s.depth_scale, (float)z16);

@@ -13,14 +13,20 @@
 // interval and the integers agree.  Pixels that fail the test, pixels nearer than the guard depth and taps outside the
 // staged window are re-evaluated with the exact chain (deproject_tap<TEX_GENERAL>) -- the guard only decides WHO pays.
 //
-// Error model (u = 2^-24; gamma_k = k u / (1 - k u); standard results for recursive summation and FMA chains):
+// Error model (u = 2^-24; gamma_k = k u / (1 - k u); standard results for recursive summation and FMA chains), for the x
+// coordinate of a pixel whose normalised source coordinate is nx (y alike, with the second row of R):
 //     |t_f - t*| <= gamma_4 S,  |t_a - t*| <= gamma_3 S,   S = |R.0 p0| + |R.1 p1| + |R.2 p2| + |T|
-//     S_i / |t2| <= s_i = (a_i + |T_i| / z_g) / k'   for depths >= z_g, with a_i = |R.0| nx_max + |R.1| ny_max + |R.2|,
-//     t2 >= k' * depth,  k' = R22 - |R20| nx_max - |R21| ny_max - max(0, -T2) / z_g
+//     t2 >= k' * depth for depths >= z_g,  k' = R22 - |R20| nx_max - |R21| ny_max - max(0, -T2) / z_g
+//     |q| <= S0 / |t2| <= qb(nx) = (|R00| |nx| + |R01| ny_max + |R02| + |T0| / z_g) / k'
+//     S2 / |t2| <= s2 = (|R20| nx_max + |R21| ny_max + |R22| + |T2| / z_g) / k'
 //     rcp.approx: relative error <= 2^-22 (PTX ISA: at most 1 ulp; doubled here)
-// The bound is worst-case (every rounding error aligned) and is multiplied by PIPE_GUARD_SAFETY on top.
+//     E1 <= qb f (gamma_4 (1 + s2) / (1 - gamma_4 s2) + 5 u) + 4 u |pp| + u            (divide, scale, add, /W, fma .5)
+//     E2 <= qb f ((gamma_3 (1 + s2) + 2^-22) / (1 - gamma_3 s2 - 2^-22) + 3 u) + 2 u (|pp| + .5)
+// (times 1.01 for the second-order terms).  The bound is worst-case (every rounding error aligned), is multiplied by
+// PIPE_GUARD_SAFETY on top, and is LINEAR in |nx|: eps_x(nx) = ax + bx |nx|, so every thread of the kernel carries the
+// bound of its own columns and rows instead of the frame's corner (half the pixels at the guard, on average).
 // tests/cpp/guard_check.cpp samples both chains on random calibrations and pixels (largest observed |fx_a - tx_f|:
-// 0.3 of the bound); the GPU tests compare every byte with the oracle anyway.
+// about 0.4 of the bound); the GPU tests compare every byte with the oracle anyway.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -30,43 +36,47 @@
 namespace pcs {
 
 constexpr double PIPE_GUARD_SAFETY = 1.1;
-constexpr int PIPE_GUARD_Z16 = 64;       // z16 below this (and above 0) always takes the exact chain
-constexpr int PIPE_SEG_PX = 128;         // colour window segment: 128 px = 384 B (a multiple of 16 for the bulk copies)
+constexpr int PIPE_GUARD_Z16 = 160;      // z16 below this (and above 0) always takes the exact chain
+#ifndef PIPE_SEG_SHIFT
+#define PIPE_SEG_SHIFT 7
+#endif
+constexpr int PIPE_SEG_PX = 1 << PIPE_SEG_SHIFT;   // colour window segment: 128 px = 384 B (a multiple of 16 for the bulk copies)
 constexpr int PIPE_SEG_BYTES = PIPE_SEG_PX * 3;
-constexpr int PIPE_MAX_SEGS = 16;        // colour frames up to 2048 px wide
+constexpr int PIPE_MAX_SEGS = 2048 / PIPE_SEG_PX;  // colour frames up to 2048 px wide
 
 struct PipeGuard {
     bool ok;
-    float eps_x, eps_y;      // pixels
+    float ax, bx, ay, by;    // eps_x = ax + bx |nx|, eps_y = ay + by |ny|  (pixels)
 };
 
 template <class P>
 inline PipeGuard pipe_guard(const P &p) {
-    PipeGuard g{false, 0.f, 0.f};
+    PipeGuard g{false, 0.f, 0.f, 0.f, 0.f};
     const double u = std::ldexp(1.0, -24), g4 = 4 * u / (1 - 4 * u), g3 = 3 * u / (1 - 3 * u), er = std::ldexp(1.0, -22);
     const double nxmax = std::max(std::fabs((0.0 - p.ppx) / p.fx), std::fabs(((double)p.W - p.ppx) / p.fx));
     const double nymax = std::max(std::fabs((0.0 - p.ppy) / p.fy), std::fabs(((double)p.H - p.ppy) / p.fy));
+    const double nmax[2] = {nxmax, nymax};
     const double zg = (double)p.depth_scale * PIPE_GUARD_Z16;
     if (!(zg > 0)) return g;
     const double k = p.R[8] - std::fabs(p.R[2]) * nxmax - std::fabs(p.R[5]) * nymax - std::max(0.0, -(double)p.T[2]) / zg;
     if (!(k > 0.04)) return g;
-    double s[3];
-    for (int i = 0; i < 3; ++i)
-        s[i] = (std::fabs(p.R[i]) * nxmax + std::fabs(p.R[3 + i]) * nymax + std::fabs(p.R[6 + i]) + std::fabs(p.T[i]) / zg) / k;
+    const double s2 = (std::fabs(p.R[2]) * nxmax + std::fabs(p.R[5]) * nymax + std::fabs(p.R[8]) + std::fabs(p.T[2]) / zg) / k;
+    if (!(g4 * s2 < 0.01)) return g;
+    const double C = 1.01 * (g4 * (1 + s2) / (1 - g4 * s2) + (g3 * (1 + s2) + er) / (1 - g3 * s2 - er) + 8 * u);
     const double f[2] = {std::fabs(p.cfx), std::fabs(p.cfy)}, pp[2] = {std::fabs(p.cppx), std::fabs(p.cppy)};
-    double eps[2];
+    double a[2], b[2];
     for (int i = 0; i < 2; ++i) {
-        const double q = s[i], pm = q * f[i] + pp[i];
-        const double dq_exact = 1.01 * ((g4 * s[i] + q * g4 * s[2]) / (1 - g4 * s[2]) + u * q);
-        const double e1 = f[i] * dq_exact + 1.01 * (2 * u * pm) + 1.01 * (2 * u * pm + u);
-        const double dq_apx = 1.01 * ((g3 * s[i] + q * (g3 * s[2] + er)) / (1 - g3 * s[2] - er) + u * q);
-        const double e2 = f[i] * dq_apx + 1.01 * (2 * u * (pm + 0.5));
-        eps[i] = PIPE_GUARD_SAFETY * (e1 + e2) + 1e-5;
+        // row i of R (column-major storage): own-axis coefficient R[4 i + ... ] -> R[i + 3 i] = R[4 i]; the other one R[i + 3 (1 - i)]
+        const double own = std::fabs(p.R[i + 3 * i]), other = std::fabs(p.R[i + 3 * (1 - i)]);
+        const double alpha = own / k, beta = (other * nmax[1 - i] + std::fabs(p.R[6 + i]) + std::fabs(p.T[i]) / zg) / k;
+        const double d0 = 1.01 * (4 * u * pp[i] + u + 2 * u * (pp[i] + 0.5));
+        a[i] = PIPE_GUARD_SAFETY * (beta * f[i] * C + d0) + 1e-5;
+        b[i] = PIPE_GUARD_SAFETY * alpha * f[i] * C;
+        if (!(a[i] + b[i] * nmax[i] < 0.05)) return g;     // a guard that wide would send every pixel to the exact chain
     }
-    if (!(eps[0] < 0.05 && eps[1] < 0.05)) return g;     // a guard that wide would send every pixel to the exact chain
     g.ok = true;
-    g.eps_x = (float)eps[0];
-    g.eps_y = (float)eps[1];
+    g.ax = (float)a[0]; g.bx = (float)b[0];
+    g.ay = (float)a[1]; g.by = (float)b[1];
     return g;
 }
 

@@ -4,7 +4,7 @@
 //   * the exact chain (oracle/SPEC.md s1, every operator rounded once: what the reference's call into librealsense
 //     computes, src/pcs-camera-optimized.cpp:198-199 with :434-444 for the index), argument of trunc(), and
 //   * the cheap chain the kernel evaluates (three FMAs per component, an approximate reciprocal, one FMA to pixels),
-// for every pixel and every depth >= the guard depth.  Sampled here on random rigs (rotations up to ~1.5 degrees,
+// for every pixel (the bound is linear in the pixel's normalised source coordinate) and every depth >= the guard depth.  Sampled here on random rigs (rotations up to ~1.5 degrees,
 // translations up to 6 cm, depth and colour sensors of different sizes) with the reciprocal perturbed by up to one
 // unit in the last place in either direction (PTX rcp.approx.ftz.f32: at most 1 ulp).  Prints the largest observed
 // fraction of the bound (must stay below 1 / PIPE_GUARD_SAFETY) and exits 0 when it does.
@@ -82,13 +82,14 @@ int main(int argc, char **argv) {
             const float y0 = nudge((float)(1.0 / (double)a2), (int)(i % 3) - 1);
             const float fx = fmaf(a0 * y0, p.cfx, p.cppx + 0.5f), fy = fmaf(a1 * y0, p.cfy, p.cppy + 0.5f);
             // taps far outside the frame are clamped by both chains
-            if (tx > -4 && tx < p.CW + 4) worst_rig = std::max(worst_rig, std::fabs((double)fx - (double)tx) / g.eps_x);
-            if (ty > -4 && ty < p.CH + 4) worst_rig = std::max(worst_rig, std::fabs((double)fy - (double)ty) / g.eps_y);
+            const double eps_x = g.ax + g.bx * std::fabs(nx), eps_y = g.ay + g.by * std::fabs(ny);
+            if (tx > -4 && tx < p.CW + 4) worst_rig = std::max(worst_rig, std::fabs((double)fx - (double)tx) / eps_x);
+            if (ty > -4 && ty < p.CH + 4) worst_rig = std::max(worst_rig, std::fabs((double)fy - (double)ty) / eps_y);
         }
         worst = std::max(worst, worst_rig);
         if (rig < 8 || worst_rig > 0.5)
-            printf("rig %2d  %dx%d -> %dx%d  eps = %.2e, %.2e px   largest |cheap - exact| / eps = %.3f\n", rig, p.W, p.H, p.CW,
-                   p.CH, g.eps_x, g.eps_y, worst_rig);
+            printf("rig %2d  %dx%d -> %dx%d  eps_x = %.2e + %.2e |nx|, eps_y = %.2e + %.2e |ny| px   largest |cheap - exact| / eps = %.3f\n",
+                   rig, p.W, p.H, p.CW, p.CH, g.ax, g.bx, g.ay, g.by, worst_rig);
     }
     printf("%d rigs (%d refused by pipe_guard), %lld samples each: largest fraction of the bound %.3f (limit %.3f)\n", rigs, refused,
            samples, worst, 1.0 / pcs::PIPE_GUARD_SAFETY);

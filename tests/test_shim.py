@@ -114,3 +114,19 @@ def test_division_by_constant_is_correctly_rounded():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout
     assert " 0 mismatches" in r.stdout
+
+
+def test_guard_bound_dominates_the_distance_between_the_two_tap_chains():
+    """Rotated depth->colour calibrations: the pipelined kernel accepts the tap of a cheap projection chain where it
+    stays eps away from every integer (pcs_guard.h).  Sample the exact and the cheap chain on random rigs and check
+    that their distance stays below the bound the host derives (largest observed fraction well under 1)."""
+    src = os.path.join(ROOT, "tests", "cpp", "guard_check.cpp")
+    exe = os.path.join(os.path.dirname(BIN), "guard_check")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["/usr/bin/g++", "-O2", "-mfma", "-ffp-contract=off", "-I",
+                    os.path.join(ROOT, "pointcloud_stitching_b200", "csrc"), src, "-o", exe],
+                   check=True, capture_output=True, text=True)
+    r = subprocess.run([exe, "60", "300000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout
+    frac = float(r.stdout.strip().splitlines()[-1].split("largest fraction of the bound")[1].split()[0])
+    assert 0.1 < frac < 0.7, r.stdout       # neither violated nor vacuous
