@@ -62,7 +62,7 @@ def parse():
     ap.add_argument("--configs", default="c3,c5", help="extra BASELINE configs measured into the same line ('none' to skip)")
     ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the sustained K1 leg (0 to skip)")
     ap.add_argument("--e2e-slots", type=int, default=2, choices=[1, 2, 3, 4], help="stitched frames in flight in the e2e leg")
-    ap.add_argument("--merge-lanes", type=int, default=4, help="c3 / c5 at N = 1: stitched frames merged concurrently")
+    ap.add_argument("--merge-lanes", type=int, default=8, help="c3 / c5 at N = 1: stitched frames merged concurrently")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the stitched-bytes verification")
