@@ -388,3 +388,84 @@ def test_error_paths(ctx0):
     t = torch.zeros(1280 * 720 + 8, dtype=torch.int16, device="cuda")
     with pytest.raises(pcs.PcsError):                            # misaligned depth pointer
         ctx0.batch([(5, t.data_ptr() + 2, t.data_ptr(), t.data_ptr())])
+
+
+# ------------------------------------------------------------------ guarded taps: edge geometries
+ROT_EDGE = {
+    # a frame lower than a segment window is tall, segments of the last partial 128 px, a single row
+    "rot_256x8": dict(w=256, h=8, rotation=small_rotation(0.002, -0.001, 0.004), translation=(0.015, 0.0002, 0.0)),
+    "rot_200x1": dict(w=200, h=1, rotation=small_rotation(0.001, 0.001, -0.002), translation=(0.012, 0.0, 0.0001)),
+    # 2048-px colour (16 segments, the most the table holds) behind a 1024-px depth frame, padded colour stride
+    "rot_1024x64_color2048": dict(w=1024, h=64, cw=2048, ch=128, stride=2048 * 3 + 64,
+                                  rotation=small_rotation(-0.002, 0.002, 0.003), translation=(0.02, 0.0003, -0.0002)),
+    # colour SMALLER than depth: several depth rows tap the same colour row
+    "rot_848x480_color424": dict(w=848, h=480, cw=424, ch=240, rotation=small_rotation(0.003, 0.002, -0.004),
+                                 translation=(0.015, 0.0, 0.0)),
+    # negative T.z and a strong x baseline: t2 shrinks for near points, the guard depth handles them
+    "rot_640x360_tz_negative": dict(w=640, h=360, rotation=small_rotation(0.004, 0.004, 0.004), translation=(0.05, 0.001, -0.004)),
+}
+
+
+@pytest.mark.parametrize("case", list(ROT_EDGE))
+def test_guarded_taps_edge_geometries(ctx, R, case):
+    kw = dict(ROT_EDGE[case])
+    w, h = kw.pop("w"), kw.pop("h")
+    cw, ch = kw.pop("cw", w), kw.pop("ch", h)
+    stride = kw.pop("stride", cw * 3)
+    cal, desc = calib_and_desc(w, h, cw, ch, tf=synth.TF_STITCH[4], stride=stride, **kw)
+    ctx.set_stream(0, desc)
+    jobs = []
+    for f in range(3):
+        # very near depths (under the guard depth), far ones and holes in one frame
+        z = synth.depth_frame(w, h, 5, f, lo=1 if f == 0 else 300, hi=900 if f == 0 else 6000)
+        jobs.append((0, z, synth.color_frame(cw, ch, 5, f, stride=stride)))
+    try:
+        got = run_batch(ctx, jobs, None)
+    except pcs.PcsError as e:       # kernel_variant 2 may refuse a geometry, never return wrong bytes
+        assert ctx.variant == 2 and e.status == pcs.PCS_ERR_UNSUPPORTED
+        return
+    for (_, z, col), (rec, _, _) in zip(jobs, got):
+        want = R.frame(cal, z, col, 3, stride, synth.TF_STITCH[4])
+        bad = np.nonzero((rec != want).any(axis=1))[0]
+        assert bad.size == 0, "first mismatches at points %s: got %s want %s" % (bad[:5], rec[bad[:5]], want[bad[:5]])
+
+
+def test_transform_changed_under_a_live_batch_and_many_streams(R):
+    """The camera->world transforms of a pipelined launch travel in the kernel parameters (64 slots per launch): 70
+    streams with 70 different transforms split the batch into two launches, and a transform set AFTER the batch was
+    created must be the one the next run uses (include/pcs_b200.h: only tf may change under a live batch)."""
+    w, h, n_streams = 256, 16, 70
+    ctx = pcs.Context(device=0, max_streams=n_streams, kernel_variant=2)
+    rng = np.random.default_rng(5)
+
+    def tf_of(k):
+        t = synth.TF_STITCH[k % 8].copy()
+        t[3], t[7], t[11] = 0.01 * k, -0.02 * k, 0.005 * k
+        return t
+
+    for rot in (None, small_rotation(0.002, 0.001, -0.003)):
+        cal = None
+        for k in range(n_streams):
+            cal, desc = calib_and_desc(w, h, tf=tf_of(k), translation=synth.D2C_BASELINE, rotation=rot)
+            ctx.set_stream(k, desc)
+        z = synth.depth_frame(w, h, 1, 1)
+        col = synth.color_frame(w, h, 1, 1)
+        dz, dc = torch.from_numpy(z.view(np.int16)).cuda(), torch.from_numpy(col).cuda()
+        pays = [torch.zeros(w * h * 5, dtype=torch.int16, device="cuda") for _ in range(n_streams)]
+        b = ctx.batch([(k, dz.data_ptr(), dc.data_ptr(), pays[k].data_ptr()) for k in range(n_streams)])
+        assert b.launches == 2
+        b.run(torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        for k in (0, 1, 63, 64, 69):
+            assert np.array_equal(pays[k].cpu().numpy().reshape(-1, 5), R.frame(cal, z, col, 3, w * 3, tf_of(k)))
+        # new transforms for two streams, one in each launch; same batch
+        for k in (3, 66):
+            _, desc = calib_and_desc(w, h, tf=tf_of(k + 100), translation=synth.D2C_BASELINE, rotation=rot)
+            ctx.set_stream(k, desc)
+        b.run(torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        for k in (3, 66):
+            assert np.array_equal(pays[k].cpu().numpy().reshape(-1, 5), R.frame(cal, z, col, 3, w * 3, tf_of(k + 100)))
+        assert np.array_equal(pays[4].cpu().numpy().reshape(-1, 5), R.frame(cal, z, col, 3, w * 3, tf_of(4)))
+        b.close()
+    del rng
