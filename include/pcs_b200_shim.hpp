@@ -12,6 +12,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cctype>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -104,26 +105,30 @@ inline bool load_transform(const std::string &path, const std::string &camera, f
     size_t at = 0;
     while ((at = text.find(key, at)) != std::string::npos) {
         size_t p = at + key.size();
-        while (p < text.size() && (text[p] == ' ' || text[p] == '\n' || text[p] == '\r' || text[p] == '\t')) ++p;
-        if (p < text.size() && text[p] == ':') {      // a key, not a value that happens to match
-            ++p;
-            int n = 0;
-            while (p < text.size() && n < 16) {
-                const char c = text[p];
-                if (c == '[' || c == ',' || c == ' ' || c == '\n' || c == '\r' || c == '\t') { ++p; continue; }
-                if (c == ']') {                        // rows close with ']'; "]]" ends the matrix
-                    ++p;
-                    continue;
-                }
-                char *end = nullptr;
-                const double v = std::strtod(text.c_str() + p, &end);
-                if (end == text.c_str() + p) break;    // not a number: malformed
-                tf[n++] = (float)v;
-                p = (size_t)(end - text.c_str());
-            }
-            return n == 16;
+        while (p < text.size() && std::isspace((unsigned char)text[p])) ++p;
+        if (p >= text.size() || text[p] != ':') { at = p; continue; }      // a value that happens to match, not a key
+        ++p;
+        // the value: numbers inside brackets (4 rows of 4, 3 rows of 4, or flat), nothing else; it ends where the
+        // brackets close, so a short matrix never borrows numbers from the next entry
+        int n = 0, depth = 0;
+        bool opened = false, bad = false;
+        float v16[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1};
+        while (p < text.size() && !(opened && depth == 0)) {
+            const char c = text[p];
+            if (std::isspace((unsigned char)c) || c == ',') { ++p; continue; }
+            if (c == '[') { ++depth; opened = true; ++p; continue; }
+            if (c == ']') { --depth; ++p; continue; }
+            char *end = nullptr;
+            const double v = std::strtod(text.c_str() + p, &end);
+            if (!opened || end == text.c_str() + p || n == 16 || !(v == v)) { bad = true; break; }
+            v16[n++] = (float)v;
+            p = (size_t)(end - text.c_str());
         }
-        at = p;
+        if (!bad && opened && depth == 0 && (n == 16 || n == 12)) {     // 12: the last row (0 0 0 1) is implied
+            std::memcpy(tf, v16, sizeof v16);
+            return true;
+        }
+        return false;
     }
     return false;
 }

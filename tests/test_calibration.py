@@ -68,4 +68,18 @@ def test_cxx_host_loads_the_same_transforms(tmp_path):
         got = np.array([int(x, 16) for x in r.stdout.split()], np.uint32).view(np.float32)
         assert np.array_equal(got, want[name]), name
     assert subprocess.run([exe, str(js), "NOPE"], capture_output=True, text=True).returncode == 1
+    # files other tools write: one line, 3 x 4 (last row implied), a short matrix followed by more numbers, a camera
+    # name that also occurs as a value
+    other = tmp_path / "other.json"
+    other.write_text('{"note":"LEVO","short":[[1,2,3],[4,5,6]],"n":[7,8,9,10,11,12,13,14,15,16],'
+                     '"LEVO":[[1,0,0,0.5],[0,1,0,-2e0],[0,0,1,3]],\n"flat" : [1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16],'
+                     '"text":["a"]}')
+    r = subprocess.run([exe, str(other), "LEVO"], capture_output=True, text=True)
+    got = np.array([int(x, 16) for x in r.stdout.split()], np.uint32).view(np.float32)
+    assert r.returncode == 0 and np.array_equal(got, np.float32([1, 0, 0, .5, 0, 1, 0, -2, 0, 0, 1, 3, 0, 0, 0, 1]))
+    r = subprocess.run([exe, str(other), "flat"], capture_output=True, text=True)
+    got = np.array([int(x, 16) for x in r.stdout.split()], np.uint32).view(np.float32)
+    assert r.returncode == 0 and np.array_equal(got, np.arange(1, 17, dtype=np.float32))
+    for name in ("short", "n", "text", "note"):       # 6 numbers, 10 numbers, not numbers, not a matrix
+        assert subprocess.run([exe, str(other), name], capture_output=True, text=True).returncode == 1, name
     assert subprocess.run([exe, str(tmp_path / "missing.json"), "LEVO"], capture_output=True).returncode == 1
