@@ -61,13 +61,17 @@ typedef enum pcs_status {
 } pcs_status;
 
 /* rs2_intrinsics.  model / coeffs follow rs2_distortion: 0 = none (D400 depth: all coefficients zero),
- * 1 = modified Brown-Conrady (applied when a point is projected: the colour intrinsics),
- * 2 = inverse Brown-Conrady (applied when a pixel is deprojected: the depth intrinsics); coeffs = k1, k2, p1, p2, k3.
- * Streams with a distortion model run the general kernel (the arithmetic is oracle/SPEC.md s1's restatement of
- * librealsense's rsutil.h, parity unpinned like the rest of the deprojection).  A zero-initialised tail means "none". */
+ * 1 = modified Brown-Conrady (applied when a point is PROJECTED: it matters on the colour intrinsics),
+ * 2 = inverse Brown-Conrady (applied when a pixel is DEPROJECTED: it matters on the depth intrinsics),
+ * 4 = Brown-Conrady (a rectified image: never applied); coeffs = k1, k2, p1, p2, k3.  As in librealsense's rsutil.h a
+ * model on the side of the chain that does not apply it is accepted and has no effect (a D455 colour stream reports
+ * inverse Brown-Conrady); F-Theta (3) and Kannala-Brandt (5) are refused with PCS_ERR_UNSUPPORTED.
+ * Streams whose distortion does apply run the general kernel (the arithmetic is oracle/SPEC.md s1's restatement of
+ * rsutil.h, parity unpinned like the rest of the deprojection).  A zero-initialised tail means "none". */
 #define PCS_B200_DISTORTION_NONE 0
 #define PCS_B200_DISTORTION_MODIFIED_BROWN_CONRADY 1
 #define PCS_B200_DISTORTION_INVERSE_BROWN_CONRADY 2
+#define PCS_B200_DISTORTION_BROWN_CONRADY 4
 typedef struct pcs_intrinsics {
     int32_t width, height;
     float ppx, ppy, fx, fy;

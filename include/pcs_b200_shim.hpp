@@ -48,8 +48,10 @@ private:
 
 // rs2_intrinsics -> pcs_intrinsics, distortion included (templated so that this header does not need librealsense2:
 // any struct with rs2_intrinsics' members works).  librealsense's rs2_distortion numbers NONE = 0, MODIFIED_BROWN_CONRADY
-// = 1, INVERSE_BROWN_CONRADY = 2 -- the values of PCS_B200_DISTORTION_*; BROWN_CONRADY (4: the image is already
-// rectified, rsutil.h applies nothing) maps to none, the fisheye models pass through and pcs_b200_set_stream refuses them.
+// = 1, INVERSE_BROWN_CONRADY = 2, BROWN_CONRADY = 4 -- the values of PCS_B200_DISTORTION_*; a model with all-zero
+// coefficients maps to none, everything else passes through: the library applies a model where rsutil.h does (inverse
+// Brown-Conrady when deprojecting, modified Brown-Conrady when projecting), ignores it where rsutil.h does, and
+// pcs_b200_set_stream refuses the fisheye models.
 template <class Rs2Intrinsics>
 inline pcs_intrinsics intrinsics_from_rs2(const Rs2Intrinsics &in) {
     pcs_intrinsics o;
@@ -59,7 +61,7 @@ inline pcs_intrinsics intrinsics_from_rs2(const Rs2Intrinsics &in) {
     const int model = (int)in.model;
     bool any = false;
     for (int i = 0; i < 5; ++i) any = any || in.coeffs[i] != 0.f;
-    o.model = (model == 4 || !any) ? PCS_B200_DISTORTION_NONE : model;
+    o.model = any ? model : PCS_B200_DISTORTION_NONE;
     if (o.model != PCS_B200_DISTORTION_NONE)
         for (int i = 0; i < 5; ++i) o.coeffs[i] = in.coeffs[i];
     return o;

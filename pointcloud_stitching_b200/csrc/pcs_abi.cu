@@ -180,7 +180,10 @@ bool is_identity3(const float *r) {
 
 // Choose the cheapest tex-coordinate path that is still bit-exact (pcs_device.cuh).
 int pick_tex_mode(const pcs_stream_desc &d) {
-    if (d.depth.model != PCS_B200_DISTORTION_NONE || d.color.model != PCS_B200_DISTORTION_NONE) return TEX_GENERAL;
+    // (librealsense applies inverse Brown-Conrady only when deprojecting and modified Brown-Conrady only when projecting;
+    // the other way round the coefficients have no effect)
+    if (d.depth.model == PCS_B200_DISTORTION_INVERSE_BROWN_CONRADY || d.color.model == PCS_B200_DISTORTION_MODIFIED_BROWN_CONRADY)
+        return TEX_GENERAL;
     if (!is_identity3(d.d2c_rotation)) return TEX_GENERAL;
     const bool t0 = d.d2c_translation[0] == 0.f && d.d2c_translation[1] == 0.f &&
                     d.d2c_translation[2] == 0.f;
@@ -235,7 +238,8 @@ void digest(const pcs_stream_desc &d, StreamParams &p) {
     memcpy(p.R, d.d2c_rotation, sizeof p.R);
     memcpy(p.T, d.d2c_translation, sizeof p.T);
     memcpy(p.tf, d.tf, sizeof p.tf);
-    p.dmodel = d.depth.model; p.cmodel = d.color.model;
+    p.dmodel = d.depth.model == PCS_B200_DISTORTION_INVERSE_BROWN_CONRADY ? d.depth.model : 0;
+    p.cmodel = d.color.model == PCS_B200_DISTORTION_MODIFIED_BROWN_CONRADY ? d.color.model : 0;
     memcpy(p.dcoef, d.depth.coeffs, sizeof p.dcoef);
     memcpy(p.ccoef, d.color.coeffs, sizeof p.ccoef);
     p.cutoff = d.cutoff != 0; p.lane_rev = d.cutoff_lane_reversed != 0;
@@ -448,10 +452,14 @@ int pcs_b200_set_stream(pcs_ctx *ctx, int stream, const pcs_stream_desc *desc) {
     if (d.depth.width < 0 || d.depth.height < 0 ||
         (long long)d.depth.width * d.depth.height > (1ll << 28))
         return fail(ctx, PCS_ERR_INVALID, "bad depth geometry");
-    // librealsense applies inverse Brown-Conrady when deprojecting and modified Brown-Conrady when projecting
-    if ((d.depth.model != PCS_B200_DISTORTION_NONE && d.depth.model != PCS_B200_DISTORTION_INVERSE_BROWN_CONRADY) ||
-        (d.color.model != PCS_B200_DISTORTION_NONE && d.color.model != PCS_B200_DISTORTION_MODIFIED_BROWN_CONRADY))
-        return fail(ctx, PCS_ERR_UNSUPPORTED, "distortion models: depth none / inverse Brown-Conrady, colour none / modified Brown-Conrady");
+    // rsutil.h (2.16): rs2_deproject_pixel_to_point undistorts for INVERSE_BROWN_CONRADY only, rs2_project_point_to_pixel
+    // distorts for MODIFIED_BROWN_CONRADY only; a model on the other side of the chain (a D455 colour stream reports
+    // inverse Brown-Conrady) or plain BROWN_CONRADY (a rectified image) is carried and ignored there, as here.  The
+    // fisheye models (F-Theta 3, Kannala-Brandt 5) are not implemented: refused, not ignored.
+    auto known = [](int m) { return m == PCS_B200_DISTORTION_NONE || m == PCS_B200_DISTORTION_MODIFIED_BROWN_CONRADY ||
+                                    m == PCS_B200_DISTORTION_INVERSE_BROWN_CONRADY || m == PCS_B200_DISTORTION_BROWN_CONRADY; };
+    if (!known(d.depth.model) || !known(d.color.model))
+        return fail(ctx, PCS_ERR_UNSUPPORTED, "distortion models: none, (modified / inverse) Brown-Conrady; not F-Theta / Kannala-Brandt");
     DeviceGuard dg_(ctx->device);
     StreamState &s = ctx->streams[stream];
     std::lock_guard<std::mutex> lk(s.mu);

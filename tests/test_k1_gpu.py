@@ -2,6 +2,8 @@
 (a) the golden fixtures produced by the reference's own compiled functions and
 (b) the oracle restatement on full-size seeded frames.  Bit-exact on all 10
 bytes of every record; float XYZ within 1e-5 relative (north_star)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -376,7 +378,7 @@ def test_error_paths(ctx0):
         ctx0.set_stream(5, bad)
     assert e.value.status == pcs.PCS_ERR_UNSUPPORTED
     bad = pcs.stream_desc(64, 4, depth_distortion=(0.1, 0, 0, 0, 0))
-    bad.depth.model = 1                                           # modified Brown-Conrady belongs to projection
+    bad.depth.model = 5                                           # Kannala-Brandt
     with pytest.raises(pcs.PcsError) as e:
         ctx0.set_stream(5, bad)
     assert e.value.status == pcs.PCS_ERR_UNSUPPORTED
@@ -469,3 +471,19 @@ def test_transform_changed_under_a_live_batch_and_many_streams(R):
         assert np.array_equal(pays[4].cpu().numpy().reshape(-1, 5), R.frame(cal, z, col, 3, w * 3, tf_of(4)))
         b.close()
     del rng
+
+
+def test_distortion_on_the_side_that_does_not_apply_it_has_no_effect(ctx, R):
+    """rsutil.h undistorts only when deprojecting (inverse Brown-Conrady) and distorts only when projecting (modified
+    Brown-Conrady): a D455 colour stream reports inverse Brown-Conrady coefficients, which rs2_project_point_to_pixel
+    ignores.  Such a stream is accepted, keeps the fast kernels and gives the bytes of the undistorted calibration."""
+    w, h = 848, 480
+    cal, plain = calib_and_desc(w, h, tf=synth.TF_STITCH[2], translation=synth.D2C_BASELINE)
+    _, desc = calib_and_desc(w, h, tf=synth.TF_STITCH[2], translation=synth.D2C_BASELINE)
+    desc.color.model, desc.color.coeffs = 2, (C.c_float * 5)(-0.05, 0.06, 0.0003, -0.0004, -0.02)      # inverse BC on colour
+    desc.depth.model, desc.depth.coeffs = 4, (C.c_float * 5)(0.1, 0.1, 0.0, 0.0, 0.0)                   # plain BC on depth
+    ctx.set_stream(0, desc)
+    z, col = synth.depth_frame(w, h, 4, 4), synth.color_frame(w, h, 4, 4)
+    (rec, _, _), = run_batch(ctx, [(0, z, col)], None)       # (kernel_variant 2 accepts it: still the x-baseline mode)
+    assert np.array_equal(rec, R.frame(cal, z, col, 3, w * 3, synth.TF_STITCH[2]))
+    del plain
