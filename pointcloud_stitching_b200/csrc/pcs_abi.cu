@@ -123,7 +123,9 @@ struct pcs_batch {
     };
     std::vector<Group> groups;
     struct CutJob { int job, n, lane_rev, n_tiles; int32_t *d_tiles; };
-    std::vector<CutJob> cuts;
+    std::vector<CutJob> cuts;       // -c jobs (their look-back words live in d_lb)
+    void *d_lb = nullptr;           // look-back words of every -c job of the batch: one memset per run
+    size_t lb_bytes = 0;
     std::vector<std::pair<int, unsigned>> gens;   // (stream, geom_gen) captured at create
     std::vector<void *> owned;          // scratch to free
     int launches = 0;
@@ -275,7 +277,7 @@ int ensure_frame_buffers(pcs_ctx *ctx, StreamState &s) {
         if ((rc = grow(ctx, s.d_z16, n))) return rc;
         if ((rc = grow(ctx, s.d_payload, n * 5))) return rc;
         if ((rc = grow(ctx, s.d_dense, n * 5))) return rc;
-        if ((rc = grow(ctx, s.d_keep, n))) return rc;
+        if ((rc = grow(ctx, s.d_keep, n + 64))) return rc;      // (-c: the look-back words of the one-pass compaction)
         if ((rc = grow(ctx, s.d_tiles, n / CMP_TILE + 2))) return rc;
         s.cap_pts = n;
     }
@@ -325,6 +327,7 @@ void launch_k1_direct(int tex_mode, bool cutoff, bool floatout, dim3 grid, cudaS
 }
 
 int tiles_for(int n_pts) { return (n_pts / 8 + K1_THREADS - 1) / K1_THREADS; }
+
 
 }  // namespace
 
@@ -539,13 +542,11 @@ int pcs_b200_send_xyzrgb_begin(pcs_ctx *ctx, int stream, const uint16_t *z16_hos
     CU(ctx, cudaMemcpyAsync(s.d_z16, z16_host, (size_t)p.N * 2, cudaMemcpyHostToDevice, s.cs));
     CU(ctx, cudaMemcpyAsync(s.d_color, color_host, (size_t)p.CH * p.stride, cudaMemcpyHostToDevice, s.cs));
     dim3 grid(tiles_for(p.N), 1);
+    if (p.cutoff) CU(ctx, cudaMemsetAsync(s.d_keep, 0, (size_t)(tiles_for(p.N) + 1) * 4, s.cs));    // look-back words
     launch_k1_direct(p.tex_mode, p.cutoff, false, grid, s.cs, s.d_job, ctx->d_params);
     CU(ctx, cudaGetLastError());
     uint8_t *dst = reinterpret_cast<uint8_t *>(buffer_host) + PCS_B200_HEADER_BYTES;
     if (p.cutoff) {
-        rc = launch_compaction(ctx, s.d_keep, s.d_dense, p.N, p.lane_rev, s.d_tiles, s.d_payload,
-                               s.d_count, s.cs);
-        if (rc < 0) return rc;
         CU(ctx, cudaMemcpyAsync(s.h_count, s.d_count, 4, cudaMemcpyDeviceToHost, s.cs));
         // the count is only known on the device: the records are copied out in end()
     } else {
@@ -720,21 +721,25 @@ static int batch_create_impl(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs
         d.z16 = in.z16_dev; d.color = in.color_dev; d.payload = in.payload_dev;
         d.xyzrgb = in.xyzrgb_dev; d.count = in.count_dev; d.stream = in.stream;
         if (p.cutoff) {
-            void *dense = nullptr, *keep = nullptr, *tiles = nullptr;
-            const int n_tiles = (p.N + CMP_TILE - 1) / CMP_TILE;
-            if (cudaMalloc(&dense, (size_t)p.N * 10 + 64) != cudaSuccess ||
-                cudaMalloc(&keep, (size_t)p.N + 64) != cudaSuccess ||
-                cudaMalloc(&tiles, (size_t)(n_tiles + 2) * 4) != cudaSuccess) {
-                cudaGetLastError();
-                cudaFree(dense); cudaFree(keep); cudaFree(tiles);
-                return bail(fail(ctx, PCS_ERR_NOMEM, "cutoff scratch allocation failed"));
-            }
-            b->owned.push_back(dense); b->owned.push_back(keep); b->owned.push_back(tiles);
-            d.dense = (int16_t *)dense; d.keep = (uint8_t *)keep;
-            b->cuts.push_back({(int)b->jobs.size(), p.N, p.lane_rev, n_tiles, (int32_t *)tiles});
+            // look-back words of the one-pass compaction (k1_direct<CUTOFF>): [ticket][one per tile], 16-byte slices of
+            // one allocation for the whole batch (offset kept in d_tiles until the buffer exists)
+            const int n_tiles = tiles_for(p.N);
+            b->cuts.push_back({(int)b->jobs.size(), p.N, p.lane_rev, n_tiles, reinterpret_cast<int32_t *>(b->lb_bytes)});
+            b->lb_bytes += ((size_t)(n_tiles + 1) * 4 + 15) & ~(size_t)15;
         }
         b->jobs.push_back(d);
         b->gens.emplace_back(in.stream, ctx->streams[in.stream].geom_gen);
+    }
+    if (b->lb_bytes) {
+        if (cudaMalloc(&b->d_lb, b->lb_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return bail(fail(ctx, PCS_ERR_NOMEM, "cutoff scratch allocation failed"));
+        }
+        b->owned.push_back(b->d_lb);
+        for (auto &c : b->cuts) {
+            c.d_tiles = reinterpret_cast<int32_t *>(static_cast<uint8_t *>(b->d_lb) + reinterpret_cast<size_t>(c.d_tiles));
+            b->jobs[c.job].keep = reinterpret_cast<uint8_t *>(c.d_tiles);
+        }
     }
     if (cudaMalloc(&b->d_jobs, sizeof(DevJob) * b->jobs.size()) != cudaSuccess) {
         cudaGetLastError();
@@ -767,7 +772,7 @@ static int batch_create_impl(pcs_ctx *ctx, const pcs_frame_job *jobs, int n_jobs
     }
     if (n_peers && !b->use_pipe)
         return bail(fail(ctx, PCS_ERR_UNSUPPORTED, "the fused exchange needs the pipelined kernel (kernel_variant != 1)"));
-    b->launches = b->use_pipe ? pipe_launches(b->pipe) : (int)b->groups.size() + 3 * (int)b->cuts.size();
+    b->launches = b->use_pipe ? pipe_launches(b->pipe) : (int)b->groups.size();
     *out = b;
     return PCS_OK;
 }
@@ -898,17 +903,13 @@ int pcs_b200_batch_run(pcs_ctx *ctx, pcs_batch *b, void *cuda_stream) {
         CU(ctx, cudaGetLastError());
         return PCS_OK;
     }
+    if (b->d_lb) CU(ctx, cudaMemsetAsync(b->d_lb, 0, b->lb_bytes, cs));      // tickets and tile words of the -c jobs
     for (const auto &g : b->groups) {
         dim3 grid(g.max_tiles, g.count);
         launch_k1_direct(g.tex_mode, g.cutoff != 0, g.floatout != 0, grid, cs, b->d_jobs + g.first,
                          ctx->d_params);
     }
     CU(ctx, cudaGetLastError());
-    for (const auto &c : b->cuts) {
-        const DevJob &j = b->jobs[c.job];
-        int rc = launch_compaction(ctx, j.keep, j.dense, c.n, c.lane_rev, c.d_tiles, j.payload, j.count, cs);
-        if (rc < 0) return rc;
-    }
     return PCS_OK;
 }
 

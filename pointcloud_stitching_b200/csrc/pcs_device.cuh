@@ -172,6 +172,15 @@ __device__ __forceinline__ void deproject_tap(const S &s, uint32_t z16, int x, i
     yi = tex_to_pixel(v, s.chf, s.CH - 1);
 }
 
+// The vertex's x and z alone (what the -c test looks at), exactly as deproject_tap computes them.
+template <int MODE, class S>
+__device__ __forceinline__ void deproject_xz(const S &s, uint32_t z16, float nx, float ny, float &p0, float &p2) {
+    const float depth = __fmul_rn(s.depth_scale, (float)z16);
+    if (MODE == TEX_GENERAL && s.dmodel == 2) bc_deproject(s.dcoef, nx, ny);
+    p0 = __fmul_rn(depth, nx);
+    p2 = depth;
+}
+
 // src/pcs-camera-optimized.cpp:499-511 on the pre-transform vertex.
 __device__ __forceinline__ bool cutoff_keep(const StreamParams &s, float x, float z) {
     return z > s.z_lo && z <= s.z_hi && x > s.x_lo && x <= s.x_hi;

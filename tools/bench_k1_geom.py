@@ -31,7 +31,12 @@ CASES = [
           rotation=(0.99988, 0.0149, 0.0051, -0.0150, 0.99984, 0.0099, -0.0049, -0.0100, 0.99994)), 64),
     ("1280x720 depth + 1920x1080 colour (windowed pipelined kernel)", dict(w=1280, h=720, cw=1920, ch=1080,
                                                                           translation=synth.D2C_BASELINE), 64),
+    # the reference's -c flag (src/pcs-camera-optimized.cpp:499-577): keep flags + order-preserving compaction
+    ("1280x720 baseline, -c cutoff (z in (0, 1.5], x in (-2, 2])", dict(w=1280, h=720, translation=synth.D2C_BASELINE, cutoff=True), 64),
+    ("1280x720 baseline, RGBA colour (general kernel)", dict(w=1280, h=720, translation=synth.D2C_BASELINE, bpp=4), 64),
 ]
+if len(sys.argv) > 1:
+    CASES = [c for c in CASES if any(a in c[0] for a in sys.argv[1:])]
 
 
 def main():
@@ -45,10 +50,11 @@ def main():
         ctx.set_stream(0, pcs.stream_desc(w, h, tf=synth.TF_STITCH[0], **kw))
         distinct = min(n_frames, 48)      # enough distinct input that a launch streams from HBM
         z = torch.from_numpy(np.stack([synth.depth_frame(w, h, 0, f) for f in range(distinct)]).view(np.int16)).cuda()
-        c = torch.from_numpy(np.stack([synth.color_frame(cw, ch, 0, f) for f in range(distinct)])).cuda()
+        c = torch.from_numpy(np.stack([synth.color_frame(cw, ch, 0, f, bpp=kw.get("bpp", 3)) for f in range(distinct)])).cuda()
         pay = torch.zeros(n_frames * w * h * 5, dtype=torch.int16, device="cuda")
-        jobs = [(0, z[f % distinct].data_ptr(), c[f % distinct].data_ptr(), pay.data_ptr() + f * w * h * 10)
-                for f in range(n_frames)]
+        cnt = torch.zeros(n_frames, dtype=torch.int32, device="cuda")
+        jobs = [(0, z[f % distinct].data_ptr(), c[f % distinct].data_ptr(), pay.data_ptr() + f * w * h * 10, None,
+                 cnt.data_ptr() + 4 * f) for f in range(n_frames)]
         b = ctx.batch(jobs)
         for _ in range(3):
             b.run(cs)
@@ -61,14 +67,15 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         pts = n_frames * w * h
-        alg = pts * (2 + 10) + n_frames * cw * ch * 3
-        res.append({"case": name, "frames_per_launch": n_frames, "launches": b.launches, "ms": ms,
+        kept = int(cnt.sum().item())
+        alg = pts * 2 + kept * 10 + n_frames * cw * ch * kw.get("bpp", 3)
+        res.append({"case": name, "frames_per_launch": n_frames, "launches": b.launches, "ms": ms, "records_kept": kept / pts,
                     "mpoints_s": pts / ms / 1e3, "GBps": alg / ms / 1e6, "frac_of_copy_peak": alg / ms / 1e6 / PEAK})
         print(res[-1])
         b.close()
         ctx.close()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "k1_geom.json"), "w"), indent=1)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "k1_geom.json" if len(sys.argv) == 1 else "k1_geom_part.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
