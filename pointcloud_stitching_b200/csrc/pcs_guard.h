@@ -84,9 +84,10 @@ inline PipeGuard pipe_guard(const P &p) {
 // optical axis shears the tap rows along x (5 mrad: 6 rows across 1280 px) and the other two axes bend them (terms in
 // x*y and y*y, about a row across a 720p frame), so one window of whole colour rows per tile would have to be several rows
 // taller than the tile.  Instead every (depth row, segment) gets the exact range of colour rows its taps can reach for
-// depths >= 0.2 m -- sampled on the host in double, every 4th column, eight depths, 0.05 rows of slack; a tap outside
+// depths >= z_near -- sampled on the host in double, every 4th column, eight depths, 0.05 rows of slack; a tap outside
 // costs an exact re-evaluation with a global load, never a wrong byte -- and a tile stages, per segment, the union
-// over its rows.
+// over its rows.  z_near is 0.2 m unless a y offset between the sensors makes the windows of such near points tall (the
+// parallax grows with 1 / z): then 0.3 or 0.45 m, whichever first brings a depth row's window down to 4 colour rows.
 struct PipeSegWindow {
     bool ok = false;
     int n_segs = 0, H = 0;
@@ -94,7 +95,7 @@ struct PipeSegWindow {
 };
 
 template <class P>
-inline PipeSegWindow pipe_seg_window(const P &p) {
+inline PipeSegWindow pipe_seg_window(const P &p, double z_near = 0.2) {
     PipeSegWindow w;
     w.n_segs = (p.CW + PIPE_SEG_PX - 1) / PIPE_SEG_PX;
     w.H = p.H;
@@ -102,7 +103,7 @@ inline PipeSegWindow pipe_seg_window(const P &p) {
     const int NONE = 1 << 30;
     w.lo.assign((size_t)p.H * w.n_segs, NONE);
     w.hi.assign((size_t)p.H * w.n_segs, -NONE);
-    const double zs[] = {0.2, 0.25, 0.35, 0.5, 1.0, 2.0, 4.0, 65.0};
+    const double zs[] = {z_near, z_near * 1.25, z_near * 1.75, z_near * 2.5, std::max(1.0, z_near * 4), std::max(2.0, z_near * 8), 8.0, 65.0};
     for (int y = 0; y < p.H; ++y) {
         int *lo = &w.lo[(size_t)y * w.n_segs], *hi = &w.hi[(size_t)y * w.n_segs];
         const double ny = ((double)y - p.ppy) / p.fy;
