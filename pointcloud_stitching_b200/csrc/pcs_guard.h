@@ -6,8 +6,9 @@
 //     xi = trunc(fma(u, CW, .5)) clamped,  u = fl(px / CW),  px = fl(fl(q * cfx) + cppx),  q = fl(t0 / t2),
 //     t = R p + T evaluated left to right, one rounding per operator
 // -- fifteen roundings whose only product is an INTEGER.  The kernel therefore evaluates a cheaper chain
-//     t_a = fma(R.0, p0, fma(R.1, p1, fma(R.2, p2, T)));  fx_a = fma(t0_a * rcp.approx(t2_a), cfx, cppx + .5)
-// and accepts trunc(fx_a) only where fx_a keeps a distance eps from every integer, with eps >= E1 + E2:
+//     t_a = fma(R.0, p0, fma(R.1, p1, fma(R.2, p2, T)));  fx_a = fma(t0_a * rcp.approx(t2_a), cfx, cppx) + 1/2
+// (the 1/2 is never added: the kernel takes rint(fx_a - 1/2), which equals trunc(fx_a) away from the integers, out of the
+// guard's own magic-number add) and accepts it only where fx_a keeps a distance eps from every integer, with eps >= E1 + E2:
 //     E1 = |exact float chain - value in real arithmetic|,  E2 = |cheap chain - value in real arithmetic|
 // (both chains start from the SAME floats p0, p1, p2).  Then the exact chain's argument of trunc lies in the same unit
 // interval and the integers agree.  Pixels that fail the test, pixels nearer than the guard depth and taps outside the

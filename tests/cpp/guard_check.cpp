@@ -80,7 +80,8 @@ int main(int argc, char **argv) {
             const float a1 = fmaf(p.R[1], p0, fmaf(p.R[4], p1, fmaf(p.R[7], d, p.T[1])));
             const float a2 = fmaf(p.R[2], p0, fmaf(p.R[5], p1, fmaf(p.R[8], d, p.T[2])));
             const float y0 = nudge((float)(1.0 / (double)a2), (int)(i % 3) - 1);
-            const float fx = fmaf(a0 * y0, p.cfx, p.cppx + 0.5f), fy = fmaf(a1 * y0, p.cfy, p.cppy + 0.5f);
+            // (the kernel never adds the 1/2: it rounds fx - 1/2 to nearest where the guard passes)
+            const double fx = (double)fmaf(a0 * y0, p.cfx, p.cppx) + 0.5, fy = (double)fmaf(a1 * y0, p.cfy, p.cppy) + 0.5;
             // taps far outside the frame are clamped by both chains
             const double eps_x = g.ax + g.bx * std::fabs(nx), eps_y = g.ay + g.by * std::fabs(ny);
             if (tx > -4 && tx < p.CW + 4) worst_rig = std::max(worst_rig, std::fabs((double)fx - (double)tx) / eps_x);
