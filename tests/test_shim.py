@@ -130,3 +130,17 @@ def test_guard_bound_dominates_the_distance_between_the_two_tap_chains():
     assert r.returncode == 0, r.stdout
     frac = float(r.stdout.strip().splitlines()[-1].split("largest fraction of the bound")[1].split()[0])
     assert 0.1 < frac < 0.7, r.stdout       # neither violated nor vacuous
+
+
+def test_segment_windows_hold_every_tap_of_a_rotated_rig():
+    """pcs_guard.h: the colour rows staged per depth row and 128-px segment must hold the tap of every pixel at every depth
+    beyond the near limit (8 M random pixels over four geometries, the rig of `bench.py --tex rotated`), and stay as short
+    as DESIGN.md says (3-4 rows per depth row)."""
+    src = os.path.join(ROOT, "tests", "cpp", "guard_window_main.cpp")
+    exe = os.path.join(os.path.dirname(BIN), "guard_window")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++11", "-I", os.path.join(ROOT, "pointcloud_stitching_b200", "csrc"), src, "-o", exe],
+                   check=True, capture_output=True, text=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    assert r.stdout.count("misses 0 of") == 4, r.stdout
