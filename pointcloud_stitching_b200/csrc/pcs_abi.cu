@@ -39,7 +39,7 @@ struct StreamState {
     uint16_t *d_z16 = nullptr;
     uint8_t *d_color = nullptr;
     int16_t *d_payload = nullptr;   // N records (compacted when cutoff)
-    int16_t *d_dense = nullptr;     // cutoff scratch
+    int16_t *d_dense = nullptr;     // (unused since the one-pass -c of k1_direct: no dense records any more)
     uint8_t *d_keep = nullptr;
     int32_t *d_tiles = nullptr;
     int32_t *d_count = nullptr;
@@ -276,7 +276,6 @@ int ensure_frame_buffers(pcs_ctx *ctx, StreamState &s) {
         s.cap_pts = 0;   // a failed grow leaves null pointers: never trust the old capacity afterwards
         if ((rc = grow(ctx, s.d_z16, n))) return rc;
         if ((rc = grow(ctx, s.d_payload, n * 5))) return rc;
-        if ((rc = grow(ctx, s.d_dense, n * 5))) return rc;
         if ((rc = grow(ctx, s.d_keep, n + 64))) return rc;      // (-c: the look-back words of the one-pass compaction)
         if ((rc = grow(ctx, s.d_tiles, n / CMP_TILE + 2))) return rc;
         s.cap_pts = n;
@@ -537,7 +536,7 @@ int pcs_b200_send_xyzrgb_begin(pcs_ctx *ctx, int stream, const uint16_t *z16_hos
     if ((rc = ensure_frame_buffers(ctx, s))) return rc;
     DevJob job{};
     job.z16 = s.d_z16; job.color = s.d_color; job.payload = s.d_payload; job.xyzrgb = nullptr;
-    job.count = s.d_count; job.keep = s.d_keep; job.dense = s.d_dense; job.stream = stream;
+    job.count = s.d_count; job.keep = s.d_keep; job.dense = nullptr; job.stream = stream;
     CU(ctx, cudaMemcpyAsync(s.d_job, &job, sizeof job, cudaMemcpyHostToDevice, s.cs));
     CU(ctx, cudaMemcpyAsync(s.d_z16, z16_host, (size_t)p.N * 2, cudaMemcpyHostToDevice, s.cs));
     CU(ctx, cudaMemcpyAsync(s.d_color, color_host, (size_t)p.CH * p.stride, cudaMemcpyHostToDevice, s.cs));

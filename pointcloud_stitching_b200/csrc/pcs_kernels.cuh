@@ -24,8 +24,8 @@ struct DevJob {
     int16_t *payload;
     float *xyzrgb;     // optional 16 B/pt output
     int32_t *count;    // optional record count
-    uint8_t *keep;     // cutoff: per-point keep flags (scratch)
-    int16_t *dense;    // cutoff: uncompacted records (scratch); payload receives the compaction
+    uint8_t *keep;     // -c: the frame's look-back words (uint32: [0] ticket, [1 + t] tile t), zeroed before the launch
+    int16_t *dense;    // (unused: the one-pass -c writes compacted records straight into payload)
     int32_t stream;
     int32_t pad;
 };
