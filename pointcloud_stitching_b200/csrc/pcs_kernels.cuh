@@ -67,141 +67,166 @@ __device__ __forceinline__ void warp_store_records(uint4 *slab, const uint32_t (
 // job.keep points at the frame's look-back words, zeroed by the host before the launch: [0] ticket, [1 + t] tile t.
 constexpr uint32_t K1C_AGG = 1u << 30, K1C_PREFIX = 2u << 30, K1C_VALUE = (1u << 30) - 1;
 
-// The -c form of a k1_direct block (see the comment above k1_direct).  Phase 1: depth -> (x, z) of the eight points, the
-// cutoff tests, the tile's count, its status word, the look-back -- everything the other tiles wait for happens before
-// the expensive part.  Phase 2: taps, transform and packing ONLY for the points that are kept (with the bounds of
-// src/pcs-camera-optimized.cpp:398-401 most warps of a frame keep nothing and skip it), each record written straight
-// to its compacted place in shared memory.  Phase 3: the tile's run leaves with 16-byte stores.
+// The -c form of a k1_direct block (see the comment above k1_direct): persistent, software-pipelined over the tiles it
+// claims by ticket.  A block holds two tiles: A -- counted, its status word published -- and B -- claimed, its depth on the
+// way.  One trip of the loop: claim C and request its depth; PHASE 1 of B: depth -> (x, z) of the eight points per
+// thread, the cutoff tests, the tile's count, its status word (everything another tile waits for, and nothing of it waits
+// for anybody); then A is finished: look-back over the status words (its predecessors published theirs at least one trip
+// ago: no waiting in the steady state), PHASE 2: taps, transform and packing ONLY for the points A keeps (with the bounds of
+// src/pcs-camera-optimized.cpp:398-401 most warps of a frame keep nothing and skip it), each record written straight to
+// its compacted place in shared memory, PHASE 3: the run leaves with 16-byte stores.  Waiting only ever points from a tile
+// to tiles claimed before it, and every claimed tile publishes its count without waiting: no deadlock, whatever else runs
+// on the device and however few blocks are resident.
 template <int MODE, bool FLOATOUT>
 __device__ __forceinline__ void k1_direct_cutoff(const DevJob &job, const StreamParams &sp, uint32_t *lb, int octets, int lane,
-                                                 int warp, uint4 *slab0, uint32_t &s_base, uint32_t *s_warp) {
-    // tiles are taken by ticket: a tile's predecessors were claimed by blocks that are running or done, whatever else
-    // shares the device (a fixed block -> tile map would need every block of the frame resident at once, which
-    // concurrent launches on other streams can prevent)
+                                                 int warp, uint4 *slab0, uint32_t &s_base, uint32_t &s_claim, uint32_t *s_warp) {
     const int n_tiles = (octets + K1_THREADS - 1) / K1_THREADS;
-    if (threadIdx.x == 0) s_base = atomicAdd(lb, 1u);
+    if (threadIdx.x == 0) s_claim = atomicAdd(lb, 1u);
     __syncthreads();
-    const int tile = (int)s_base;
-    __syncthreads();          // (s_base is written again after the look-back)
-    if (tile >= n_tiles) return;
-    const int o = tile * K1_THREADS + (int)threadIdx.x;
-    const bool active = o < octets;
-    const int p0i = o * 8;
-    const int y = active ? p0i / sp.W : 0, x0 = active ? p0i - y * sp.W : 0;
-    uint32_t dz[4] = {0, 0, 0, 0};
-    if (active) {
-        const uint4 d = ld_global_nc_v4(job.z16 + p0i);
-        dz[0] = d.x; dz[1] = d.y; dz[2] = d.z; dz[3] = d.w;
-    }
-    float ny = 0.f;
-    uint32_t tests = 0;      // bit k: point k of the octet passes the cutoff test
-    if (active) {
-        ny = __fdiv_rn(__fsub_rn((float)y, sp.ppy), sp.fy);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t z16 = (k & 1) ? (dz[k >> 1] >> 16) : (dz[k >> 1] & 0xFFFFu);
-            const float nx = __fdiv_rn(__fsub_rn((float)(x0 + k), sp.ppx), sp.fx);
-            float p0, p2;
-            deproject_xz<MODE>(sp, z16, nx, ny, p0, p2);
-            if (cutoff_keep(sp, p0, p2)) tests |= 1u << k;
-        }
-    }
-    // bit k of kept: record k of the octet survives (gated by the test of point k ^ 3 with reversed lanes)
-    uint32_t kept = tests;
-    if (sp.lane_rev) {
-        kept = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) kept |= ((tests >> (k ^ 3)) & 1u) << k;
-    }
-    const uint32_t c = __popc(kept);
-    uint32_t inc = c;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    if (lane == 31) s_warp[warp] = inc;
+    int tileB = (int)s_claim;
     __syncthreads();
-    uint32_t before = 0, total = 0;
+    if (tileB >= n_tiles) return;
+    uint4 dB = make_uint4(0, 0, 0, 0);
+    if (tileB * K1_THREADS + (int)threadIdx.x < octets)
+        dB = ld_global_nc_v4(job.z16 + ((size_t)tileB * K1_THREADS + threadIdx.x) * 8);
+    int tileA = -1;
+    uint32_t dzA[4] = {0, 0, 0, 0}, keptA = 0, offA = 0, totalA = 0;
+    for (;;) {
+        const bool haveB = tileB < n_tiles;
+        if (threadIdx.x == 0) s_claim = haveB ? atomicAdd(lb, 1u) : (uint32_t)n_tiles;
+        // ---- phase 1 of B
+        const uint32_t dzB[4] = {dB.x, dB.y, dB.z, dB.w};
+        uint32_t keptB = 0;
+        {
+            const int o = tileB * K1_THREADS + (int)threadIdx.x;
+            if (haveB && o < octets) {
+                const int p0i = o * 8, y = p0i / sp.W, x0 = p0i - y * sp.W;
+                const float ny = __fdiv_rn(__fsub_rn((float)y, sp.ppy), sp.fy);
+                uint32_t tests = 0;      // bit k: point k of the octet passes the cutoff test
 #pragma unroll
-    for (int v = 0; v < K1_THREADS / 32; ++v) {
-        const uint32_t t = s_warp[v];
-        if (v < warp) before += t;
-        total += t;
-    }
-    const uint32_t off = before + inc - c;          // records kept before this thread's, inside the tile
-    if (warp == 0) {
-        uint32_t psum = 0;
-        if (tile > 0) {
-            if (lane == 0) *(volatile uint32_t *)(lb + 1 + tile) = K1C_AGG | total;
-            int at = tile - 1;
-            for (;;) {
-                const int t = at - lane;
-                const uint32_t v = t >= 0 ? *(volatile const uint32_t *)(lb + 1 + t) : K1C_PREFIX;
-                const uint32_t f = v >> 30;
-                const uint32_t unready = __ballot_sync(0xffffffffu, f == 0), full = __ballot_sync(0xffffffffu, f == 2);
-                const int stop = full ? __ffs(full) - 1 : 31;
-                if (unready & (0xffffffffu >> (31 - stop))) { __nanosleep(64); continue; }
-                uint32_t a = lane <= stop ? (v & K1C_VALUE) : 0u;
-#pragma unroll
-                for (int d = 16; d; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
-                psum += a;
-                if (full) break;
-                at -= 32;
-            }
-        }
-        if (lane == 0) {
-            *(volatile uint32_t *)(lb + 1 + tile) = K1C_PREFIX | (psum + total);
-            s_base = psum;
-            if (tile == n_tiles - 1 && job.count) *job.count = (int32_t)(psum + total);
-        }
-    }
-    __syncthreads();
-    // the kept records, in shared memory shifted by the destination's offset inside its 16 bytes
-    uint8_t *dst0 = reinterpret_cast<uint8_t *>(job.payload) + (size_t)s_base * 10;
-    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(dst0) & 15);
-    uint8_t *stage = reinterpret_cast<uint8_t *>(slab0);
-    const uint32_t need = (FLOATOUT && job.xyzrgb) ? (active ? 0xFFu : 0u) : kept;     // float output stays dense
-    if (need) {
-        uint16_t *out = reinterpret_cast<uint16_t *>(stage + sh + (size_t)off * 10);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if ((need >> k) & 1u) {
-                const uint32_t z16 = (k & 1) ? (dz[k >> 1] >> 16) : (dz[k >> 1] & 0xFFFFu);
-                const int x = x0 + k;
-                const float nx = __fdiv_rn(__fsub_rn((float)x, sp.ppx), sp.fx);
-                float p0, p1, p2;
-                int xi, yi;
-                deproject_tap<MODE>(sp, z16, x, y, nx, ny, p0, p1, p2, xi, yi);
-                const uint32_t rgb = load_rgb(job.color, xi * sp.bpp + yi * sp.stride);
-                if (FLOATOUT && job.xyzrgb) {
-                    float4 f;
-                    f.x = affine_row(sp.tf, 0, p0, p1, p2);
-                    f.y = affine_row(sp.tf, 1, p0, p1, p2);
-                    f.z = affine_row(sp.tf, 2, p0, p1, p2);
-                    f.w = __uint_as_float(0xFF000000u | ((rgb & 0xFF) << 16) | (rgb & 0xFF00) | ((rgb >> 16) & 0xFF));
-                    reinterpret_cast<float4 *>(job.xyzrgb)[p0i + k] = f;
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t z16 = (k & 1) ? (dzB[k >> 1] >> 16) : (dzB[k >> 1] & 0xFFFFu);
+                    const float nx = __fdiv_rn(__fsub_rn((float)(x0 + k), sp.ppx), sp.fx);
+                    float p0, p2;
+                    deproject_xz<MODE>(sp, z16, nx, ny, p0, p2);
+                    if (cutoff_keep(sp, p0, p2)) tests |= 1u << k;
                 }
-                if ((kept >> k) & 1u) {
-                    const Rec r = make_record(sp.tf, p0, p1, p2, rgb);
-                    out[0] = (uint16_t)r.a; out[1] = (uint16_t)(r.a >> 16);
-                    out[2] = (uint16_t)r.b; out[3] = (uint16_t)(r.b >> 16);
-                    out[4] = (uint16_t)r.c;
-                    out += 5;
+                // bit k of kept: record k of the octet survives (gated by the test of point k ^ 3 with reversed lanes)
+                keptB = tests;
+                if (sp.lane_rev) {
+                    keptB = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) keptB |= ((tests >> (k ^ 3)) & 1u) << k;
                 }
             }
         }
+        const uint32_t cB = __popc(keptB);
+        uint32_t inc = cB;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        const int tileC = (int)s_claim;
+        uint4 dC = make_uint4(0, 0, 0, 0);
+        if (tileC < n_tiles && tileC * K1_THREADS + (int)threadIdx.x < octets)
+            dC = ld_global_nc_v4(job.z16 + ((size_t)tileC * K1_THREADS + threadIdx.x) * 8);
+        uint32_t before = 0, totalB = 0;
+#pragma unroll
+        for (int v = 0; v < K1_THREADS / 32; ++v) {
+            const uint32_t t = s_warp[v];
+            if (v < warp) before += t;
+            totalB += t;
+        }
+        const uint32_t offB = before + inc - cB;          // records kept before this thread's, inside the tile
+        if (haveB && tileB > 0 && threadIdx.x == 0) *(volatile uint32_t *)(lb + 1 + tileB) = K1C_AGG | totalB;
+        // ---- A: look-back, records, out
+        if (tileA >= 0) {
+            if (warp == 0) {
+                uint32_t psum = 0;
+                if (tileA > 0) {
+                    int at = tileA - 1;
+                    for (;;) {
+                        const int t = at - lane;
+                        const uint32_t v = t >= 0 ? *(volatile const uint32_t *)(lb + 1 + t) : K1C_PREFIX;
+                        const uint32_t f = v >> 30;
+                        const uint32_t unready = __ballot_sync(0xffffffffu, f == 0), full = __ballot_sync(0xffffffffu, f == 2);
+                        const int stop = full ? __ffs(full) - 1 : 31;
+                        if (unready & (0xffffffffu >> (31 - stop))) { __nanosleep(64); continue; }
+                        uint32_t a = lane <= stop ? (v & K1C_VALUE) : 0u;
+#pragma unroll
+                        for (int d = 16; d; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+                        psum += a;
+                        if (full) break;
+                        at -= 32;
+                    }
+                }
+                if (lane == 0) {
+                    *(volatile uint32_t *)(lb + 1 + tileA) = K1C_PREFIX | (psum + totalA);
+                    s_base = psum;
+                    if (tileA == n_tiles - 1 && job.count) *job.count = (int32_t)(psum + totalA);
+                }
+            }
+            __syncthreads();
+            // the kept records, in shared memory shifted by the destination's offset inside its 16 bytes
+            uint8_t *dst0 = reinterpret_cast<uint8_t *>(job.payload) + (size_t)s_base * 10;
+            const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(dst0) & 15);
+            uint8_t *stage = reinterpret_cast<uint8_t *>(slab0);
+            const int o = tileA * K1_THREADS + (int)threadIdx.x;
+            const bool active = o < octets;
+            const uint32_t need = (FLOATOUT && job.xyzrgb) ? (active ? 0xFFu : 0u) : keptA;     // float output stays dense
+            if (need) {
+                const int p0i = o * 8, y = p0i / sp.W, x0 = p0i - y * sp.W;
+                const float ny = __fdiv_rn(__fsub_rn((float)y, sp.ppy), sp.fy);
+                uint16_t *out = reinterpret_cast<uint16_t *>(stage + sh + (size_t)offA * 10);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if ((need >> k) & 1u) {
+                        const uint32_t z16 = (k & 1) ? (dzA[k >> 1] >> 16) : (dzA[k >> 1] & 0xFFFFu);
+                        const int x = x0 + k;
+                        const float nx = __fdiv_rn(__fsub_rn((float)x, sp.ppx), sp.fx);
+                        float p0, p1, p2;
+                        int xi, yi;
+                        deproject_tap<MODE>(sp, z16, x, y, nx, ny, p0, p1, p2, xi, yi);
+                        const uint32_t rgb = load_rgb(job.color, xi * sp.bpp + yi * sp.stride);
+                        if (FLOATOUT && job.xyzrgb) {
+                            float4 f;
+                            f.x = affine_row(sp.tf, 0, p0, p1, p2);
+                            f.y = affine_row(sp.tf, 1, p0, p1, p2);
+                            f.z = affine_row(sp.tf, 2, p0, p1, p2);
+                            f.w = __uint_as_float(0xFF000000u | ((rgb & 0xFF) << 16) | (rgb & 0xFF00) | ((rgb >> 16) & 0xFF));
+                            reinterpret_cast<float4 *>(job.xyzrgb)[p0i + k] = f;
+                        }
+                        if ((keptA >> k) & 1u) {
+                            const Rec r = make_record(sp.tf, p0, p1, p2, rgb);
+                            out[0] = (uint16_t)r.a; out[1] = (uint16_t)(r.a >> 16);
+                            out[2] = (uint16_t)r.b; out[3] = (uint16_t)(r.b >> 16);
+                            out[4] = (uint16_t)r.c;
+                            out += 5;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // [dst0, dst0 + bytes): 2-byte stores up to the first 16-byte boundary, 16-byte stores, 2-byte stores for the rest
+            const uint32_t bytes = totalA * 10;
+            const uint32_t head = min(bytes, (16u - sh) & 15u), body = (bytes - head) & ~15u, tail = bytes - head - body;
+            for (uint32_t i = threadIdx.x * 2; i < head; i += K1_THREADS * 2)
+                *reinterpret_cast<uint16_t *>(dst0 + i) = *reinterpret_cast<const uint16_t *>(stage + sh + i);
+            for (uint32_t i = threadIdx.x * 16; i < body; i += K1_THREADS * 16)
+                st_global_v4(dst0 + head + i, *reinterpret_cast<const uint4 *>(stage + sh + head + i));
+            for (uint32_t i = threadIdx.x * 2; i < tail; i += K1_THREADS * 2)
+                *reinterpret_cast<uint16_t *>(dst0 + head + body + i) = *reinterpret_cast<const uint16_t *>(stage + sh + head + body + i);
+        }
+        __syncthreads();      // s_warp, s_claim and the stage are written again by the next trip
+        if (!haveB) break;    // (A was the last tile this block held)
+        tileA = tileB; keptA = keptB; offA = offB; totalA = totalB;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dzA[q] = dzB[q];
+        tileB = tileC; dB = dC;
     }
-    __syncthreads();
-    // [dst0, dst0 + bytes): 2-byte stores up to the first 16-byte boundary, 16-byte stores, 2-byte stores for the rest
-    const uint32_t bytes = total * 10;
-    const uint32_t head = min(bytes, (16u - sh) & 15u), body = (bytes - head) & ~15u, tail = bytes - head - body;
-    for (uint32_t i = threadIdx.x * 2; i < head; i += K1_THREADS * 2)
-        *reinterpret_cast<uint16_t *>(dst0 + i) = *reinterpret_cast<const uint16_t *>(stage + sh + i);
-    for (uint32_t i = threadIdx.x * 16; i < body; i += K1_THREADS * 16)
-        st_global_v4(dst0 + head + i, *reinterpret_cast<const uint4 *>(stage + sh + head + i));
-    for (uint32_t i = threadIdx.x * 2; i < tail; i += K1_THREADS * 2)
-        *reinterpret_cast<uint16_t *>(dst0 + head + body + i) = *reinterpret_cast<const uint16_t *>(stage + sh + head + body + i);
 }
 
 template <int MODE, bool CUTOFF, bool FLOATOUT>
@@ -209,7 +234,7 @@ __global__ void __launch_bounds__(K1_THREADS)
 k1_direct(const DevJob *__restrict__ jobs, const StreamParams *__restrict__ streams) {
     __shared__ __align__(16) uint4 slabs[K1_THREADS / 32][32 * 5 + (CUTOFF ? 1 : 0)];     // (+16 B per warp: destination alignment)
     __shared__ StreamParams sp;
-    __shared__ uint32_t s_base, s_warp[K1_THREADS / 32];
+    __shared__ uint32_t s_base, s_claim, s_warp[K1_THREADS / 32];
     const DevJob job = jobs[blockIdx.y];
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(streams + job.stream);
@@ -220,7 +245,7 @@ k1_direct(const DevJob *__restrict__ jobs, const StreamParams *__restrict__ stre
     const int octets = sp.N >> 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (CUTOFF) {
-        k1_direct_cutoff<MODE, FLOATOUT>(job, sp, reinterpret_cast<uint32_t *>(job.keep), octets, lane, warp, &slabs[0][0], s_base, s_warp);
+        k1_direct_cutoff<MODE, FLOATOUT>(job, sp, reinterpret_cast<uint32_t *>(job.keep), octets, lane, warp, &slabs[0][0], s_base, s_claim, s_warp);
         return;
     }
     const int tile0 = blockIdx.x * K1_THREADS;  // first octet of this block
