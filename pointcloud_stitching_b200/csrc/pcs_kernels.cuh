@@ -234,7 +234,12 @@ __global__ void __launch_bounds__(K1_THREADS)
 k1_direct(const DevJob *__restrict__ jobs, const StreamParams *__restrict__ streams) {
     __shared__ __align__(16) uint4 slabs[K1_THREADS / 32][32 * 5 + (CUTOFF ? 1 : 0)];     // (+16 B per warp: destination alignment)
     __shared__ StreamParams sp;
-    __shared__ uint32_t s_base, s_claim, s_warp[K1_THREADS / 32];
+    // (s_base in a 16-byte slot of its own: the compiler fetches s_claim and s_warp[] with one wide load, which must not
+    // touch a word another warp writes between the same two barriers)
+    __shared__ __align__(16) uint32_t s_base_slot[4];
+    __shared__ __align__(16) uint32_t s_cw[4 + K1_THREADS / 32];
+    uint32_t &s_base = s_base_slot[0], &s_claim = s_cw[0];
+    uint32_t *s_warp = s_cw + 4;
     const DevJob job = jobs[blockIdx.y];
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(streams + job.stream);
