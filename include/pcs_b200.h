@@ -111,7 +111,8 @@ typedef struct pcs_frame_job {
     int32_t reserved;          /* flags (0, or PCS_B200_JOB_REMOTE_FRAME: a scheduling hint, results do not depend on it) */
     const uint16_t *z16_dev;   /* depth.height * depth.width */
     const uint8_t *color_dev;  /* color.height * color_stride bytes */
-    int16_t *payload_dev;      /* depth.width*depth.height records (10 B each) */
+    int16_t *payload_dev;      /* depth.width*depth.height records (10 B each); with -c the kept records, compacted in raster
+                                * order by the same launch (bytes past *count_dev records are not written) */
     float *xyzrgb_dev;         /* optional: N x {x,y,z metres (transformed), b,g,r,255} 16 B/pt; or NULL */
     int32_t *count_dev;        /* optional: receives the record count (needed with cutoff); or NULL */
 } pcs_frame_job;
