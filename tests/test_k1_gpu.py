@@ -489,3 +489,54 @@ def test_distortion_on_the_side_that_does_not_apply_it_has_no_effect(ctx, R):
     (rec, _, _), = run_batch(ctx, [(0, z, col)], None)       # (kernel_variant 2 accepts it: still the x-baseline mode)
     assert np.array_equal(rec, R.frame(cal, z, col, 3, w * 3, synth.TF_STITCH[2]))
     del plain
+
+
+def test_cutoff_one_pass_edge_cases(ctx0, R):
+    """The one-pass -c of k1_direct (persistent blocks over ticketed tiles, look-back, compaction in shared memory): a batch
+    of several frames whose last tile is partial (848x480 = 198.75 tiles), a box that keeps every valid point, one that
+    keeps none, the reference's box with its reversed lanes, a rotated calibration, and payloads at every 2-byte
+    alignment inside their 16 bytes."""
+    w, h = 848, 480
+    n = w * h
+    boxes = {   # stream -> (lane_reversed, z_lo, z_hi, x_lo, x_hi, calibration kw)
+        0: (True, 0.0, 1.5, -2.0, 2.0, dict(translation=synth.D2C_BASELINE)),                   # the reference's -c
+        1: (False, 0.0, 100.0, -100.0, 100.0, dict(translation=synth.D2C_BASELINE)),            # every valid point
+        2: (False, 0.0, 1e-4, -2.0, 2.0, dict()),                                               # nothing
+        3: (False, 0.5, 2.5, -0.4, 1.1, dict(translation=(0.0149, 0.0002, -0.0003), rotation=small_rotation(0.003, -0.002, 0.004))),
+    }
+    cals = {}
+    for s, (rev, z_lo, z_hi, x_lo, x_hi, kw) in boxes.items():
+        cal, desc = calib_and_desc(w, h, tf=synth.TF_STITCH[s], cutoff=True, **kw)
+        desc.cutoff_lane_reversed, desc.z_lo, desc.z_hi, desc.x_lo, desc.x_hi = int(rev), z_lo, z_hi, x_lo, x_hi
+        ctx0.set_stream(s, desc)
+        cals[s] = cal
+    keep, jobs = [], []
+    for f in range(10):
+        s = f % 4
+        z, col = synth.depth_frame(w, h, 20 + s, f, lo=300, hi=4000), synth.color_frame(w, h, 20 + s, f)
+        dz, dc = dev(z), dev(col)
+        pay = torch.full((n * 5 + 16,), 0x5A5A, dtype=torch.int16, device="cuda")
+        cnt = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+        shift = f % 8                                              # records start 2 * shift bytes into the allocation
+        keep.append((s, z, col, dz, dc, pay, cnt, shift))
+        jobs.append((s, dz.data_ptr(), dc.data_ptr(), pay.data_ptr() + 2 * shift, None, cnt.data_ptr()))
+    b = ctx0.batch(jobs)
+    assert b.launches <= 4                                         # one launch per group of frames, none for the compaction
+    b.run(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for s, z, col, _, _, pay, cnt, shift in keep:
+        rev, z_lo, z_hi, x_lo, x_hi, _ = boxes[s]
+        xyz, uv = R.deproject(cals[s], z)
+        if rev:
+            want = R.pack(xyz, uv, col, w, h, 3, w * 3, synth.TF_STITCH[s], cutoff=True)
+        else:
+            dense = R.pack(xyz, uv, col, w, h, 3, w * 3, synth.TF_STITCH[s])
+            m = (xyz[:, 2] > np.float32(z_lo)) & (xyz[:, 2] <= np.float32(z_hi)) & (xyz[:, 0] > np.float32(x_lo)) & (xyz[:, 0] <= np.float32(x_hi))
+            want = dense[m]
+        c = int(cnt.item())
+        assert c == len(want), (s, c, len(want))
+        got = pay.cpu().numpy()
+        assert np.array_equal(got[shift:shift + c * 5].reshape(-1, 5), want), s
+        assert np.all(got[:shift] == 0x5A5A) and np.all(got[shift + c * 5:] == 0x5A5A), "wrote outside the kept records"
+    assert int(keep[2][6].item()) == 0 and int(keep[1][6].item()) == int((keep[1][1] != 0).sum())
+    b.close()
