@@ -92,6 +92,29 @@ int main(int argc, char **argv) {
             printf("rig %2d  %dx%d -> %dx%d  eps_x = %.2e + %.2e |nx|, eps_y = %.2e + %.2e |ny| px   largest |cheap - exact| / eps = %.3f\n",
                    rig, p.W, p.H, p.CW, p.CH, g.ax, g.bx, g.ay, g.by, worst_rig);
     }
+    // rigs the bound cannot cover must be refused (the kernel then never runs its cheap chain on them): a colour sensor
+    // 20 cm IN FRONT of the depth sensor (t2 <= 0 for near points), a 60-degree yaw (t2 changes sign inside the frame), a
+    // focal length that makes the bound wider than the guard could usefully be
+    {
+        Params p;
+        p.W = p.CW = 1280; p.H = p.CH = 720;
+        p.fx = p.fy = p.cfx = p.cfy = 640.f; p.ppx = p.cppx = 639.5f; p.ppy = p.cppy = 359.5f;
+        p.cwf = 1280.f; p.chf = 720.f; p.depth_scale = 0.001f;
+        const float I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        memcpy(p.R, I, sizeof I);
+        p.T[0] = 0.015f; p.T[1] = 0.f; p.T[2] = -0.2f;
+        if (pcs::pipe_guard(p).ok) { printf("accepted a rig with T.z = -0.2 m\n"); return 1; }
+        p.T[2] = 0.f;
+        const float c = 0.5f, s_ = 0.8660254f;      // yaw of 60 degrees, column-major
+        const float Y[9] = {c, 0, -s_, 0, 1, 0, s_, 0, c};
+        memcpy(p.R, Y, sizeof Y);
+        if (pcs::pipe_guard(p).ok) { printf("accepted a 60-degree yaw\n"); return 1; }
+        memcpy(p.R, I, sizeof I);
+        p.cfx = p.cfy = 4.0e5f;
+        if (pcs::pipe_guard(p).ok) { printf("accepted a bound wider than 0.05 px\n"); return 1; }
+        p.cfx = p.cfy = 640.f;
+        if (!pcs::pipe_guard(p).ok) { printf("refused the plain x-baseline rig\n"); return 1; }
+    }
     printf("%d rigs (%d refused by pipe_guard), %lld samples each: largest fraction of the bound %.3f (limit %.3f)\n", rigs, refused,
            samples, worst, 1.0 / pcs::PIPE_GUARD_SAFETY);
     return worst < 1.0 / pcs::PIPE_GUARD_SAFETY && refused < rigs ? 0 : 1;
